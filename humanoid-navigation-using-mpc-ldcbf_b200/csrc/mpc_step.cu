@@ -1,0 +1,142 @@
+// K2+K3 kernel (one thread per scenario) and the C-ABI entry points for one batched MPC step.
+// See mpc_qp.cuh for the formulation and the reference lines each piece replaces.
+#include <mutex>
+
+#include "mpc_qp.cuh"
+
+namespace ldcbf {
+
+static thread_local cudaError_t g_last_error = cudaSuccess;
+void set_last_error(cudaError_t e) { g_last_error = e; }
+
+struct StepIO {
+    const double* x0; const double* theta0; const double* goal; const int8_t* foot;
+    const double* c_eta; const int32_t* nobs; const double* delta; const double* limits;
+    double* U; double* X; double* theta; double* omega; double* obj; int32_t* status; int32_t* iters;
+};
+
+template <int N>
+__device__ __forceinline__ void store_solution(const QpSolution<N>& S, int b, double* U, double* X, double* theta,
+                                               double* omega, double* obj, int32_t* status, int32_t* iters) {
+    double2* U2 = reinterpret_cast<double2*>(U) + (size_t)b * N;
+    double4* X4 = reinterpret_cast<double4*>(X) + (size_t)b * (N + 1);
+#pragma unroll
+    for (int k = 0; k < N; ++k) U2[k] = make_double2(S.ux[k], S.uy[k]);
+#pragma unroll
+    for (int k = 0; k <= N; ++k) X4[k] = make_double4(S.px[k], S.vx[k], S.py[k], S.vy[k]);
+#pragma unroll
+    for (int k = 0; k <= N; ++k) theta[(size_t)b * (N + 1) + k] = S.th[k];
+#pragma unroll
+    for (int k = 0; k < N; ++k) omega[(size_t)b * N + k] = S.om[k];
+    obj[b] = S.obj;
+    status[b] = S.status;
+    iters[b] = S.iters;
+}
+
+__device__ __forceinline__ void load_limits(const StepConst& C, const double* limits, int b, double& aop,
+                                            double& vmax0, double& omax, double& omin) {
+    aop = C.alpha_over_pi; vmax0 = C.v_max0; omax = C.omega_max; omin = C.omega_min;
+    if (limits) {
+        const double4 L = reinterpret_cast<const double4*>(limits)[b];
+        if (L.x == L.x) aop = L.x / 3.141592653589793;
+        if (L.y == L.y) vmax0 = L.y;
+        if (L.z == L.z) omax = L.z;
+        if (L.w == L.w) omin = L.w;
+    }
+}
+
+template <int N, int MO>
+__global__ void __launch_bounds__(128) mpc_qp_kernel(StepConst C, int B, int max_obs, StepIO io) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double4 x = reinterpret_cast<const double4*>(io.x0)[b];          // (p_x, v_x, p_y, v_y)
+    const double2 g = reinterpret_cast<const double2*>(io.goal)[b];
+    int ft[N + 1];
+#pragma unroll
+    for (int k = 0; k <= N; ++k) ft[k] = io.foot[(size_t)b * (N + 1) + k];
+    double aop, vmax0, omax, omin;
+    load_limits(C, io.limits, b, aop, vmax0, omax, omin);
+    const int nb = min(io.nobs[b], MO);
+    QpSolution<N> S;
+    solve_scenario<N, MO>(C, x.x, x.y, x.z, x.w, io.theta0[b], g.x, g.y, ft,
+                          reinterpret_cast<const double4*>(io.c_eta) + (size_t)b * max_obs, nb,
+                          io.delta ? io.delta[b] : 0.0, aop, vmax0, omax, omin, S);
+    store_solution<N>(S, b, io.U, io.X, io.theta, io.omega, io.obj, io.status, io.iters);
+}
+
+template <int N, int MO>
+static int launch_qp(const StepConst& C, int B, int max_obs, const StepIO& io, cudaStream_t st) {
+    // small batches: one warp per block so that the warps spread over all SMs (latency-bound regime);
+    // large batches: 128-thread blocks.
+    const int threads = (B >= 148 * 4 * 128) ? 128 : 32;
+    const unsigned grid = (unsigned)((B + threads - 1) / threads);
+    mpc_qp_kernel<N, MO><<<grid, threads, 0, st>>>(C, B, max_obs, io);
+    return check_launch();
+}
+
+template <int N>
+static int dispatch_obs(const StepConst& C, int B, int max_obs, const StepIO& io, cudaStream_t st) {
+    if (max_obs <= 2) return launch_qp<N, 2>(C, B, max_obs, io, st);
+    if (max_obs <= 4) return launch_qp<N, 4>(C, B, max_obs, io, st);
+    if (max_obs <= LDCBF_MAX_OBSTACLES) return launch_qp<N, 8>(C, B, max_obs, io, st);
+    return LDCBF_E_SHAPE;
+}
+
+}  // namespace ldcbf
+
+using namespace ldcbf;
+
+extern "C" int ldcbf_abi_version(void) { return LDCBF_ABI_VERSION; }
+
+extern "C" const char* ldcbf_last_cuda_error(void) { return cudaGetErrorString(g_last_error); }
+
+extern "C" void ldcbf_params_default(ldcbf_params* p) {
+    if (!p) return;
+    p->delta_t = 0.4; p->gravity = 9.81; p->com_height = 1.0; p->alpha = 3.6;      // config.yml:2-5
+    p->l_max_x = 0.10; p->l_max_y = 0.10; p->l_min_x = -0.1; p->l_min_y = -0.1;    // config.yml:6-9
+    p->v_min[0] = -0.1; p->v_min[1] = 0.1; p->v_max[0] = 0.8; p->v_max[1] = 0.4;   // config.yml:10-11
+    p->omega_max = 0.156 * 3.141592653589793; p->omega_min = -p->omega_max;        // HumanoidMpc.py:21-22
+    p->foot_offset = 0.05; p->stop_objective = 0.05;                               // HumanoidMpc.py:200,392
+    p->sampling_time = 1e-3;                                                       // HumanoidMpc.py:50
+    p->eps_active = 1e-10; p->eps_const_row = 1e-6;
+    p->max_iter = 200; p->reserved = 0;
+}
+
+extern "C" size_t ldcbf_workspace_bytes(int, int, int, int) { return 0; }
+
+extern "C" int ldcbf_mpc_qp_f64(const ldcbf_params* prm, int B, int N, int max_obs, const double* x0,
+                                const double* theta0, const double* goal, const int8_t* foot, const double* c_eta,
+                                const int32_t* nobs, const double* delta, const double* limits, double* U, double* X,
+                                double* theta, double* omega, double* obj, int32_t* status, int32_t* iters,
+                                void* cuda_stream) {
+    if (!prm || B < 0 || max_obs <= 0) return LDCBF_E_ARG;
+    if (B == 0) return LDCBF_OK;
+    if (!x0 || !theta0 || !goal || !foot || !c_eta || !nobs || !U || !X || !theta || !omega || !obj || !status || !iters)
+        return LDCBF_E_ARG;
+    const StepConst C = make_const(*prm);
+    const StepIO io{x0, theta0, goal, foot, c_eta, nobs, delta, limits, U, X, theta, omega, obj, status, iters};
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    switch (N) {
+        case 1: return dispatch_obs<1>(C, B, max_obs, io, st);
+        case 2: return dispatch_obs<2>(C, B, max_obs, io, st);
+        case 3: return dispatch_obs<3>(C, B, max_obs, io, st);
+        case 4: return dispatch_obs<4>(C, B, max_obs, io, st);
+        default: return LDCBF_E_SHAPE;
+    }
+}
+
+extern "C" int ldcbf_mpc_step_f64(const ldcbf_params* prm, int B, int N, int max_obs, int max_verts, const double* x0,
+                                  const double* theta0, const double* goal, const int8_t* foot, const double* verts,
+                                  const int32_t* nverts, const int32_t* nobs, const double* delta, const double* warm,
+                                  const double* limits, double* U, double* X, double* theta, double* omega,
+                                  double* c_eta, double* obj, int32_t* status, int32_t* iters, void* cuda_stream) {
+    (void)warm;
+    if (!prm || B < 0 || max_obs <= 0 || max_verts <= 0) return LDCBF_E_ARG;
+    if (B == 0) return LDCBF_OK;
+    if (!x0 || !c_eta) return LDCBF_E_ARG;
+    // K1 reads the CoM position straight out of the state rows (p_x, v_x, p_y, v_y): stride 4, y at +2.
+    int rc = launch_halfplanes(B, max_obs, max_verts, x0, 4, 2, verts, nverts, nobs, c_eta, cuda_stream);
+    if (rc != LDCBF_OK) return rc;
+    return ldcbf_mpc_qp_f64(prm, B, N, max_obs, x0, theta0, goal, foot, c_eta, nobs, delta, limits, U, X, theta,
+                            omega, obj, status, iters, cuda_stream);
+}

@@ -1,0 +1,164 @@
+// Closed-loop rollout: the whole step loop of HumanoidMPC.run_simulation in ONE kernel launch.
+//
+// Reference control flow restated (HumanoidNavigation/MPC/HumanoidMpc.py):
+//   :380-459  for k in range(num_inputs): half-planes at the current CoM (:387) -> stop when the previous
+//             objective < 0.05 (:392) -> foot-parity window (:401-403) -> heading schedule (:406-411) ->
+//             solve on MPC timesteps (:415-429, break on failure) -> record u_0, omega_0 (:432-433) ->
+//             integrate / hold position on sub-steps (:439-447)
+//   :74-78    mpc_step = int(DELTA_T / sampling_time) (at least 1), num_inputs = mpc_step * N_simul
+// and the sub-goal sequencing of MPC/HumanoidMPCVariants/HumanoidMPCWithRRT.py:153-181 (a fresh run per
+// sub-goal: objective memory and foot parity restart, the state carries over).
+//
+// Mapping: one thread per scenario, persistent over all its steps: no per-step launch latency, the
+// scenario's vertex rings stay in L1/L2 (832 B at the basic shape), state and active data in registers.
+// Scenarios are independent, so a block never synchronises.
+#include "halfplane_dev.cuh"
+#include "mpc_qp.cuh"
+
+namespace ldcbf {
+
+struct RolloutIO {
+    double* state; const double* goals; const int8_t* right_first; const double2* verts; const int32_t* nverts;
+    const int32_t* nobs; const double* delta; const double* limits; double* traj_X; double* traj_U;
+    int32_t* steps; int32_t* goal_steps; int32_t* status; unsigned long long* total_solves;
+};
+
+template <int N, int MO>
+__global__ void __launch_bounds__(128) rollout_kernel(StepConst C, int B, int T, int n_goals, int max_steps_per_goal,
+                                                      int substeps, int max_obs, int max_verts, RolloutIO io) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double px = io.state[5 * (size_t)b], vx = io.state[5 * (size_t)b + 1], py = io.state[5 * (size_t)b + 2],
+           vy = io.state[5 * (size_t)b + 3], th = io.state[5 * (size_t)b + 4];
+    const bool right_first = io.right_first[b] != 0;
+    const int nb = min(io.nobs[b], MO);
+    const double dl = io.delta ? io.delta[b] : 0.0;
+    double aop, vmax0, omax, omin;
+    aop = C.alpha_over_pi; vmax0 = C.v_max0; omax = C.omega_max; omin = C.omega_min;
+    if (io.limits) {
+        const double4 L = reinterpret_cast<const double4*>(io.limits)[b];
+        if (L.x == L.x) aop = L.x / 3.141592653589793;
+        if (L.y == L.y) vmax0 = L.y;
+        if (L.z == L.z) omax = L.z;
+        if (L.w == L.w) omin = L.w;
+    }
+    double* tX = io.traj_X ? io.traj_X + (size_t)b * (T + 1) * 5 : nullptr;
+    double* tU = io.traj_U ? io.traj_U + (size_t)b * T * 3 : nullptr;
+    if (tX) { tX[0] = px; tX[1] = vx; tX[2] = py; tX[3] = vy; tX[4] = th; }
+
+    int gi = 0, kstep = 0, total = 0, solves = 0, last_status = LDCBF_STATUS_SOLVED;
+    double last_obj = INFINITY, ux = 0.0, uy = 0.0;
+    for (int i = 0; i < n_goals; ++i) io.goal_steps[(size_t)b * n_goals + i] = 0;
+
+    while (gi < n_goals && total < T) {
+        if (last_obj < C.stop_objective || kstep >= max_steps_per_goal) {     // :392 / loop exhausted
+            io.goal_steps[(size_t)b * n_goals + gi] = kstep;
+            ++gi; kstep = 0; last_obj = INFINITY;
+            continue;
+        }
+        const double gx = io.goals[((size_t)b * n_goals + gi) * 2], gy = io.goals[((size_t)b * n_goals + gi) * 2 + 1];
+        double th1, om0;
+        if (kstep % substeps == 0) {
+            // half-planes at the current CoM (:387)
+            double4 ce[MO];
+#pragma unroll
+            for (int o = 0; o < MO; ++o) {
+                ce[o] = make_double4(0.0, 0.0, 0.0, 0.0);
+                if (o < nb) {
+                    const int V = min(io.nverts[(size_t)b * max_obs + o], max_verts);
+                    if (V > 0) ce[o] = halfplane_serial(px, py, io.verts + ((size_t)b * max_obs + o) * max_verts, V);
+                }
+            }
+            int ft[N + 1];
+            const int step_number = kstep / substeps;                                 // :401
+#pragma unroll
+            for (int k = 0; k <= N; ++k) ft[k] = (((step_number + k) & 1) == (right_first ? 0 : 1)) ? 1 : -1;
+            QpSolution<N> S;
+            solve_scenario<N, MO>(C, px, vx, py, vy, th, gx, gy, ft, ce, nb, dl, aop, vmax0, omax, omin, S);
+            ++solves;
+            last_status = S.status;
+            if (S.status != LDCBF_STATUS_SOLVED) {                                    // :419-429 break
+                io.goal_steps[(size_t)b * n_goals + gi] = kstep;
+                ++gi; kstep = 0; last_obj = INFINITY;
+                continue;
+            }
+            last_obj = S.obj;
+            ux = S.ux[0]; uy = S.uy[0];
+            // x_{k+1} = A x_k + B u_0 (:441-442), evaluated as the reference does
+            const double npx = C.ch * px + C.sh_over_beta * vx + (1.0 - C.ch) * ux;
+            const double nvx = C.beta_sh * px + C.ch * vx - C.beta_sh * ux;
+            const double npy = C.ch * py + C.sh_over_beta * vy + (1.0 - C.ch) * uy;
+            const double nvy = C.beta_sh * py + C.ch * vy - C.beta_sh * uy;
+            px = npx; vx = nvx; py = npy; vy = nvy;
+            th1 = S.th[1]; om0 = S.om[0];
+        } else {
+            // sub-step: only the heading advances (:443-447)
+            const double phi = atan2(gy - py, gx - px);
+            om0 = fmin(fmax(phi - th, omin), omax);
+            th1 = __dadd_rn(th, __dmul_rn(om0, C.sampling_time));
+        }
+        th = th1;
+        if (tU) { tU[3 * total] = ux; tU[3 * total + 1] = uy; tU[3 * total + 2] = om0; }
+        ++total; ++kstep;
+        if (tX) { double* x = tX + 5 * total; x[0] = px; x[1] = vx; x[2] = py; x[3] = vy; x[4] = th; }
+    }
+    if (gi < n_goals) io.goal_steps[(size_t)b * n_goals + gi] = kstep;
+    io.state[5 * (size_t)b] = px; io.state[5 * (size_t)b + 1] = vx; io.state[5 * (size_t)b + 2] = py;
+    io.state[5 * (size_t)b + 3] = vy; io.state[5 * (size_t)b + 4] = th;
+    io.steps[b] = total;
+    io.status[b] = last_status;
+    if (io.total_solves) {
+        // one atomic per warp
+        unsigned long long s = solves;
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(__activemask(), s, off);
+        if ((threadIdx.x & 31) == (__ffs(__activemask()) - 1)) atomicAdd(io.total_solves, s);
+    }
+}
+
+template <int N, int MO>
+static int launch_rollout(const StepConst& C, int B, int T, int n_goals, int msg, int sub, int max_obs, int max_verts,
+                          const RolloutIO& io, cudaStream_t st) {
+    const int threads = (B >= 148 * 4 * 128) ? 128 : 32;
+    rollout_kernel<N, MO><<<(unsigned)((B + threads - 1) / threads), threads, 0, st>>>(C, B, T, n_goals, msg, sub,
+                                                                                      max_obs, max_verts, io);
+    return check_launch();
+}
+
+template <int N>
+static int dispatch_rollout(const StepConst& C, int B, int T, int n_goals, int msg, int sub, int max_obs,
+                            int max_verts, const RolloutIO& io, cudaStream_t st) {
+    if (max_obs <= 2) return launch_rollout<N, 2>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
+    if (max_obs <= 4) return launch_rollout<N, 4>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
+    if (max_obs <= LDCBF_MAX_OBSTACLES) return launch_rollout<N, 8>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
+    return LDCBF_E_SHAPE;
+}
+
+}  // namespace ldcbf
+
+extern "C" int ldcbf_rollout_f64(const ldcbf_params* prm, int B, int N, int T, int n_goals, int max_steps_per_goal,
+                                 int max_obs, int max_verts, double* state, const double* goals,
+                                 const int8_t* right_first, const double* verts, const int32_t* nverts,
+                                 const int32_t* nobs, const double* delta, const double* limits, double* traj_X,
+                                 double* traj_U, int32_t* steps, int32_t* goal_steps, int32_t* status,
+                                 int64_t* total_solves, void* cuda_stream) {
+    using namespace ldcbf;
+    if (!prm || B < 0 || T <= 0 || n_goals <= 0 || max_steps_per_goal <= 0 || max_obs <= 0 || max_verts <= 0)
+        return LDCBF_E_ARG;
+    if (B == 0) return LDCBF_OK;
+    if (!state || !goals || !right_first || !verts || !nverts || !nobs || !steps || !goal_steps || !status)
+        return LDCBF_E_ARG;
+    const StepConst C = make_const(*prm);
+    int sub = (int)(prm->delta_t / prm->sampling_time);                      // HumanoidMpc.py:74-75
+    if (sub <= 0) sub = 1;
+    const RolloutIO io{state, goals, right_first, reinterpret_cast<const double2*>(verts), nverts, nobs, delta, limits,
+                       traj_X, traj_U, steps, goal_steps, status,
+                       reinterpret_cast<unsigned long long*>(total_solves)};
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    switch (N) {
+        case 1: return dispatch_rollout<1>(C, B, T, n_goals, max_steps_per_goal, sub, max_obs, max_verts, io, st);
+        case 2: return dispatch_rollout<2>(C, B, T, n_goals, max_steps_per_goal, sub, max_obs, max_verts, io, st);
+        case 3: return dispatch_rollout<3>(C, B, T, n_goals, max_steps_per_goal, sub, max_obs, max_verts, io, st);
+        case 4: return dispatch_rollout<4>(C, B, T, n_goals, max_steps_per_goal, sub, max_obs, max_verts, io, st);
+        default: return LDCBF_E_SHAPE;
+    }
+}

@@ -1,0 +1,11 @@
+"""ldcbf_b200 — Python binding of libldcbf_b200.so (hand-written sm_100a CUDA, C ABI in include/ldcbf_mpc.h).
+
+There is no CPU fallback: importing the solver entry points without the built library raises, and every call
+requires CUDA tensors.  Build with `python __graft_entry__.py build` (or `make -C .../csrc`).
+"""
+from .binding import (LdcbfParams, Status, abi_version, default_params, half_planes, lib, lidar_cast, mpc_qp,
+                      mpc_step, params_from_conf, probe_fp64, rollout)
+from .batched import BatchedHumanoidMPC
+
+__all__ = ["LdcbfParams", "Status", "abi_version", "default_params", "half_planes", "lib", "lidar_cast", "mpc_qp",
+           "mpc_step", "params_from_conf", "probe_fp64", "rollout", "BatchedHumanoidMPC"]

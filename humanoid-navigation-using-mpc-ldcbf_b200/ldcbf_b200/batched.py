@@ -1,0 +1,96 @@
+"""Batched front-end: B independent scenarios, one MPC step or a whole closed loop per call.
+
+This is the new caller of the C ABI next to the reference-shaped `HumanoidNavigation.MPC.HumanoidMpc.HumanoidMPC`
+(B = 1).  It owns the device-resident scenario tensors (laid out for the kernels) and pinned
+host staging buffers for the end-to-end path.
+"""
+import numpy as np
+import torch
+
+from . import binding as _b
+
+
+class BatchedHumanoidMPC:
+    """B scenarios sharing N_horizon and the solver parameters.
+
+    obstacles are given packed: verts[B,max_obs,max_verts,2] (hull vertices, CCW, zero padded), nverts[B,max_obs],
+    nobs[B] (see `scenarios.pack_rings`).  All arrays may be numpy (copied to the device once) or CUDA tensors.
+    """
+
+    def __init__(self, goal, verts, nverts, nobs, N_horizon=3, sampling_time=0.4, conf=None, delta=None,
+                 limits=None, device="cuda", **param_overrides):
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedHumanoidMPC needs a CUDA device: ldcbf_b200 has no CPU path")
+        self.device = torch.device(device)
+        self.N = int(N_horizon)
+        self.prm = (_b.params_from_conf(conf, sampling_time, **param_overrides) if conf is not None
+                    else _b.default_params(sampling_time, **param_overrides))
+        dev = self._dev
+        self.goal = dev(goal, torch.float64)
+        self.verts = dev(verts, torch.float64)
+        self.nverts = dev(nverts, torch.int32)
+        self.nobs = dev(nobs, torch.int32)
+        self.delta = None if delta is None else dev(delta, torch.float64)
+        self.limits = None if limits is None else dev(limits, torch.float64)
+        self.B = self.goal.shape[0]
+        self._out = None
+        self._pinned = None
+
+    def _dev(self, a, dtype):
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=dtype).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(self.device)
+
+    # ---- device-resident step ---------------------------------------------------------------------------
+    def step(self, x0, theta0, foot, goal=None):
+        """One MPC step for all scenarios.  x0[B,4], theta0[B], foot[B,N+1] int8 CUDA tensors.
+        Returns dict(U, X, theta, omega, c_eta, obj, status, iters) of CUDA tensors (reused between calls)."""
+        self._out = _b.mpc_step(self.prm, x0, theta0, self.goal if goal is None else goal, foot, self.verts,
+                                self.nverts, self.nobs, delta=self.delta, limits=self.limits, out=self._out)
+        return self._out
+
+    # ---- end-to-end step: host buffers in, host buffers out -----------------------------------------------
+    def step_host(self, state_host, foot_host):
+        """state_host: pinned [B,5] fp64 tensor (p_x, v_x, p_y, v_y, theta); foot_host: pinned [B,N+1] int8.
+        Copies the inputs host->device, runs the step, copies (U[:,0], X[:,1], theta[:,1], omega[:,0], obj,
+        status) back into pinned host buffers and synchronises.  Returns the dict of pinned host tensors."""
+        B, N = self.B, self.N
+        if self._pinned is None:
+            pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+            self._pinned = dict(next_state=pin((B, 5), torch.float64), u0=pin((B, 3), torch.float64),
+                                obj=pin((B,), torch.float64), status=pin((B,), torch.int32))
+            self._d_state = torch.empty((B, 5), dtype=torch.float64, device=self.device)
+            self._d_foot = torch.empty((B, N + 1), dtype=torch.int8, device=self.device)
+            self._d_next = torch.empty((B, 5), dtype=torch.float64, device=self.device)
+            self._d_u0 = torch.empty((B, 3), dtype=torch.float64, device=self.device)
+        self._d_state.copy_(state_host, non_blocking=True)
+        self._d_foot.copy_(foot_host, non_blocking=True)
+        x0 = self._d_state[:, :4].contiguous()
+        th0 = self._d_state[:, 4].contiguous()
+        o = self.step(x0, th0, self._d_foot)
+        self._d_next[:, :4] = o["X"][:, 1]
+        self._d_next[:, 4] = o["theta"][:, 1]
+        self._d_u0[:, :2] = o["U"][:, 0]
+        self._d_u0[:, 2] = o["omega"][:, 0]
+        p = self._pinned
+        p["next_state"].copy_(self._d_next, non_blocking=True)
+        p["u0"].copy_(self._d_u0, non_blocking=True)
+        p["obj"].copy_(o["obj"], non_blocking=True)
+        p["status"].copy_(o["status"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return p
+
+    @property
+    def h2d_bytes_per_step(self):
+        return self.B * (5 * 8 + (self.N + 1))
+
+    @property
+    def d2h_bytes_per_step(self):
+        return self.B * (5 * 8 + 3 * 8 + 8 + 4)
+
+    # ---- closed loop -----------------------------------------------------------------------------------------
+    def rollout(self, state, right_first, T, goals=None, max_steps_per_goal=None, record=True):
+        """Closed loop (HumanoidMpc.py:380-459) for all scenarios in one launch.  state[B,5] CUDA, updated in place."""
+        goals = self.goal[:, None, :].contiguous() if goals is None else goals
+        return _b.rollout(self.prm, state, goals, right_first, self.verts, self.nverts, self.nobs, T, N=self.N,
+                          max_steps_per_goal=max_steps_per_goal, delta=self.delta, limits=self.limits, record=record)

@@ -1,0 +1,100 @@
+"""Synthetic scenario generators for the benchmark configs of SURVEY.md §8d (host side, numpy only).
+
+Pure numpy, seeded; used by `bench.py` (inputs only — the generated arrays are handed to the CUDA path) and by
+the parity tests so both sides see identical inputs.  The obstacle shapes restate
+`/root/reference/HumanoidNavigation/Utils/ObstaclesUtils.py:21-36` (`generate_circle_like_polygon`: num_points on
+`linspace(0, 2*pi, num_points)`, i.e. the last point duplicates the first, leaving num_points-1 hull vertices) and
+the CIRCLE_OBSTACLES map of `report_simulations/Scenario.py:202-206`.
+"""
+import math
+
+import numpy as np
+
+CIRCLES = ((10, 0.5, (5.5, -1.2)), (20, 1.0, (4.0, 2.0)), (25, 1.2, (1.7, 0.0)))
+
+
+def circle_ring(num_points, radius, center):
+    """Hull vertices (counter-clockwise) of the reference's circle-like polygon: num_points-1 distinct vertices."""
+    th = np.linspace(0, 2 * np.pi, num_points)[:-1]
+    return np.column_stack((center[0] + radius * np.cos(th), center[1] + radius * np.sin(th)))
+
+
+def circle_rings(jitter=None):
+    rings = []
+    for i, (n, r, c) in enumerate(CIRCLES):
+        cc = (c[0] + (jitter[i][0] if jitter is not None else 0.0), c[1] + (jitter[i][1] if jitter is not None else 0.0))
+        rings.append(circle_ring(n, r, cc))
+    return rings
+
+
+def pack_rings(list_of_ring_lists, max_obs=None, max_verts=None):
+    """-> verts[B,max_obs,max_verts,2] (zero padded), nverts[B,max_obs] int32, nobs[B] int32."""
+    B = len(list_of_ring_lists)
+    max_obs = max_obs or max(1, max(len(r) for r in list_of_ring_lists))
+    max_verts = max_verts or max(1, max((len(p) for r in list_of_ring_lists for p in r), default=1))
+    verts = np.zeros((B, max_obs, max_verts, 2))
+    nverts = np.zeros((B, max_obs), dtype=np.int32)
+    nobs = np.zeros(B, dtype=np.int32)
+    for b, rings in enumerate(list_of_ring_lists):
+        nobs[b] = len(rings)
+        for o, ring in enumerate(rings):
+            nverts[b, o] = len(ring)
+            verts[b, o, :len(ring)] = ring
+    return verts, nverts, nobs
+
+
+def _dist_to_ring(p, ring):
+    a = ring
+    b = np.roll(ring, -1, axis=0)
+    ab = b - a
+    t = np.clip(((p - a) * ab).sum(1) / (ab * ab).sum(1), 0, 1)
+    c = a + t[:, None] * ab
+    return float(np.min(np.hypot(*(c - p).T)))
+
+
+def _inside_convex(p, ring):
+    a = ring
+    b = np.roll(ring, -1, axis=0)
+    cr = (b[:, 0] - a[:, 0]) * (p[1] - a[:, 1]) - (b[:, 1] - a[:, 1]) * (p[0] - a[:, 0])
+    return bool(np.all(cr >= 0))
+
+
+def config2(B=4096, seed=0):
+    """Batched basic simulation.
+
+    start p ~ U([-1,1]x[2,4]), v = 0, theta0 ~ U(-pi,pi), first foot ~ Bernoulli(1/2); goal ~ U([5,7]x[-4,-2]);
+    the three config-1 circles with centres jittered U(-0.25,0.25)^2; a sample is redrawn while start or goal is
+    inside / within 0.05 of a polygon.  Returns dict of arrays (state[B,5], goal[B,2], right_first[B] bool,
+    verts, nverts, nobs).
+    """
+    rng = np.random.default_rng(seed)
+    state = np.zeros((B, 5))
+    goal = np.zeros((B, 2))
+    right = np.zeros(B, dtype=bool)
+    rings_all = []
+    for b in range(B):
+        while True:
+            p = rng.uniform((-1, 2), (1, 4))
+            g = rng.uniform((5, -4), (7, -2))
+            th = rng.uniform(-math.pi, math.pi)
+            rf = rng.random() < 0.5
+            jit = rng.uniform(-0.25, 0.25, size=(3, 2))
+            rings = circle_rings(jit)
+            ok = all(not _inside_convex(q, r) and _dist_to_ring(q, r) > 0.05 for q in (p, g) for r in rings)
+            if ok:
+                break
+        state[b] = (p[0], 0.0, p[1], 0.0, th)
+        goal[b] = g
+        right[b] = rf
+        rings_all.append(rings)
+    verts, nverts, nobs = pack_rings(rings_all, 3, 24)
+    return dict(state=state, goal=goal, right_first=right, verts=verts, nverts=nverts, nobs=nobs, rings=rings_all)
+
+
+def foot_window(right_first, step, N):
+    """Parity window s_v[step:step+N+1] of HumanoidMpc.py:104-108,403 for arrays of scenarios -> int8[B,N+1]."""
+    right_first = np.asarray(right_first, dtype=bool)
+    idx = step + np.arange(N + 1)[None, :]
+    even = (idx % 2) == 0
+    s = np.where(even == right_first[:, None], 1, -1)
+    return s.astype(np.int8)

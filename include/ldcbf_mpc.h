@@ -1,0 +1,146 @@
+/*
+ * ldcbf_mpc.h — C ABI of the B200-native LDCBF-MPC hot path (libldcbf_b200.so).
+ *
+ * The reference (salvatore373/Humanoid-Navigation-using-MPC-LDCBF) has no FFI: the seam is Python method
+ * calls inside `HumanoidNavigation/MPC/HumanoidMpc.py`.  Each entry point below names the reference call
+ * site(s) it replaces (paths relative to the reference root).  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every array pointer is caller-owned, contiguous, row-major DEVICE memory unless the name ends in
+ *    `_host`; fp64 / int32 / int8 as declared; the library allocates nothing persistent;
+ *  - calls are asynchronous on `cuda_stream` (a cudaStream_t passed as void*; NULL = default stream),
+ *    re-entrant, no global state;
+ *  - return value: 0 on success, negative LDCBF_E_* on argument / launch errors (nothing is thrown);
+ *    the numerical outcome of each scenario is reported in status[b] (LDCBF_STATUS_*).
+ *  - state layout (p_x, v_x, p_y, v_y) and input layout (f_x, f_y) as in `HumanoidMpc.py:34-48`;
+ *    obstacles are convex polygons given by their hull vertices in counter-clockwise order
+ *    (`polygon.points[polygon.vertices]`, `Utils/ObstaclesUtils.py:54`), zero padded to max_verts.
+ */
+#ifndef LDCBF_MPC_H
+#define LDCBF_MPC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDCBF_ABI_VERSION 1
+
+/* return codes */
+#define LDCBF_OK 0
+#define LDCBF_E_ARG (-1)      /* null pointer / non-positive size */
+#define LDCBF_E_SHAPE (-2)    /* horizon or obstacle count not supported by the compiled kernels */
+#define LDCBF_E_LAUNCH (-3)   /* CUDA launch error (see ldcbf_last_cuda_error) */
+
+/* per-scenario status */
+#define LDCBF_STATUS_SOLVED 0
+#define LDCBF_STATUS_MAX_ITER 1
+#define LDCBF_STATUS_INFEASIBLE 2   /* reference: IPOPT raises, loop breaks (HumanoidMpc.py:419-429) */
+#define LDCBF_STATUS_DEGENERATE 3   /* CoM exactly on an obstacle edge: ||x-c|| = 0 (ObstaclesUtils.py:104) */
+#define LDCBF_STATUS_DONE 4         /* rollout only: scenario already stopped (objective < stop_objective) */
+
+/* supported shapes of the register-resident solver */
+#define LDCBF_MAX_HORIZON 4
+#define LDCBF_MAX_OBSTACLES 8
+
+/* Every key of HumanoidNavigation/config.yml:2-17 that the hot path reads, the constants the reference
+ * hard-codes, and the solver controls.  Fill with ldcbf_params_default() and override. */
+typedef struct ldcbf_params {
+    double delta_t;         /* DELTA_T        config.yml:2  */
+    double gravity;         /* GRAVITY_CONST  config.yml:3  */
+    double com_height;      /* COM_HEIGHT     config.yml:4  */
+    double alpha;           /* ALPHA          config.yml:5  */
+    double l_max_x, l_max_y, l_min_x, l_min_y;  /* config.yml:6-9 */
+    double v_min[2];        /* V_MIN          config.yml:10 */
+    double v_max[2];        /* V_MAX          config.yml:11 */
+    double omega_max;       /* 0.156*pi       HumanoidMpc.py:21 */
+    double omega_min;       /* -omega_max     HumanoidMpc.py:22 */
+    double foot_offset;     /* 0.05           HumanoidMpc.py:200 */
+    double stop_objective;  /* 0.05           HumanoidMpc.py:392 (rollout) */
+    double sampling_time;   /* ctor argument  HumanoidMpc.py:50,159 */
+    double eps_active;      /* a constraint counts as violated below -eps_active (normalised rows) */
+    double eps_const_row;   /* tolerance on the constant k = 0 LDCBF rows (1e-6, BASELINE.json) */
+    int32_t max_iter;       /* active-set iteration cap per solve */
+    int32_t reserved;
+} ldcbf_params;
+
+/* Optional per-scenario overrides of the limits `bounds_tuning.py:22-26` mutates:
+ * limits[b] = (ALPHA, V_MAX[0], OMEGA_MAX, OMEGA_MIN).  NaN entries fall back to ldcbf_params. */
+#define LDCBF_LIMITS_STRIDE 4
+
+int ldcbf_abi_version(void);
+void ldcbf_params_default(ldcbf_params* prm);
+const char* ldcbf_last_cuda_error(void);
+
+/* Workspace query kept for ABI stability; the current kernels need none (returns 0). */
+size_t ldcbf_workspace_bytes(int B, int N, int max_obs, int max_verts);
+
+/* K1 — LDCBF half-plane builder.
+ * Replaces ObstaclesUtils.get_closest_point_and_normal_vector_from_obs (Utils/ObstaclesUtils.py:60-109),
+ * is_point_inside_polygon (:50-57) and the loop of HumanoidMPC._get_list_c_and_eta (MPC/HumanoidMpc.py:296-319).
+ *   pos    [B,2]                      current CoM (p_x, p_y)
+ *   verts  [B,max_obs,max_verts,2]    hull vertices, CCW, zero padded
+ *   nverts [B,max_obs] int32, nobs [B] int32
+ *   c_eta  [B,max_obs,4] out          (c_x, c_y, eta_x, eta_y); rows o >= nobs[b] are zero */
+int ldcbf_halfplanes_f64(int B, int max_obs, int max_verts, const double* pos, const double* verts,
+                         const int32_t* nverts, const int32_t* nobs, double* c_eta, void* cuda_stream);
+
+/* K2+K3 — heading schedule, QP assembly, exact QP solve, one LIP integration, given the half-planes.
+ * Replaces _precompute_theta_omega_naive (HumanoidMpc.py:137-160), the constraint/cost builders (:162-249,
+ * :252-294, :321-333), optim_prob.solve() (:417) and _integrate (:335-343, :441-447).
+ *   x0 [B,4], theta0 [B], goal [B,2], foot [B,N+1] int8 (+1 right / -1 left, the s_v window of :403)
+ *   c_eta [B,max_obs,4], nobs [B]; delta [B] or NULL (HumanoidMPCCustomLCBF.py:30-31);
+ *   limits [B,4] or NULL
+ * out: U [B,N,2] footsteps, X [B,N+1,4] predicted states (X[:,1] is the next state), theta [B,N+1],
+ *      omega [B,N], obj [B] (value of the reference's cost incl. the constant k=0 term), status [B], iters [B].
+ * For status != 0 the U, X, obj entries are NaN. */
+int ldcbf_mpc_qp_f64(const ldcbf_params* prm, int B, int N, int max_obs, const double* x0, const double* theta0,
+                     const double* goal, const int8_t* foot, const double* c_eta, const int32_t* nobs,
+                     const double* delta, const double* limits, double* U, double* X, double* theta,
+                     double* omega, double* obj, int32_t* status, int32_t* iters, void* cuda_stream);
+
+/* One full MPC step = K1 then K2+K3 on the same stream (HumanoidMpc.py:387-447 for one k).
+ * `warm` [B,2N] or NULL is accepted for API parity with the reference's set_initial (:450-455); the exact
+ * active-set solver does not need it. */
+int ldcbf_mpc_step_f64(const ldcbf_params* prm, int B, int N, int max_obs, int max_verts, const double* x0,
+                       const double* theta0, const double* goal, const int8_t* foot, const double* verts,
+                       const int32_t* nverts, const int32_t* nobs, const double* delta, const double* warm,
+                       const double* limits, double* U, double* X, double* theta, double* omega, double* c_eta,
+                       double* obj, int32_t* status, int32_t* iters, void* cuda_stream);
+
+/* K4 — LiDAR ray casting.  Replaces compute_lidar_readings / get_closest_point
+ * (RangeFinder/range_finder_wth_polygons_dbscan.py:13-63) and line_polygon_intersection (Utils/obstacles.py:95-139).
+ *   ray_dirs [R,2]  lidar_range*(cos, sin)(i*2*pi/R) computed on the host with libm exactly as :28-37
+ *   pos [B,2]; verts/nverts/nobs as above but in the order the reference casts against
+ *   (ConvexHull.points rows, HumanoidMPCUnknownEnvironment.py:46)
+ * out: hit_obs [B,R] int32 (-1 = no hit), hit_edge [B,R] int32, hit_xy [B,R,2] (NaN = no hit). */
+int ldcbf_lidar_cast_f64(int B, int R, const double* ray_dirs, double lidar_range, const double* pos, int max_obs,
+                         int max_verts, const double* verts, const int32_t* nverts, const int32_t* nobs,
+                         int32_t* hit_obs, int32_t* hit_edge, double* hit_xy, void* cuda_stream);
+
+/* Closed loop (HumanoidMpc.py:380-459, incl. the mpc_step = int(DELTA_T/sampling_time) sub-stepping of :74-78,
+ * :384,:443-446) with optional sub-goal sequencing (HumanoidMPCVariants/HumanoidMPCWithRRT.py:153-181: a fresh
+ * run per sub-goal — objective memory and foot parity restart, the state carries over).  One kernel launch.
+ *   state  [B,5] in/out   (p_x, v_x, p_y, v_y, theta)
+ *   goals  [B,n_goals,2]; right_first [B] int8 (1 = start_with_right_foot)
+ *   T = total loop-iteration budget per scenario (size of the trajectory buffers);
+ *   max_steps_per_goal = num_inputs of one run (mpc_step * N_mpc_timesteps)
+ *   traj_X [B,T+1,5] or NULL (row 0 = initial state), traj_U [B,T,3] or NULL (f_x, f_y, omega)
+ *   steps [B] out: loop iterations executed; goal_steps [B,n_goals] out: iterations spent on each sub-goal;
+ *   status [B] out: status of the last solve; total_solves: optional device counter (+= QP solves). */
+int ldcbf_rollout_f64(const ldcbf_params* prm, int B, int N, int T, int n_goals, int max_steps_per_goal, int max_obs,
+                      int max_verts, double* state, const double* goals, const int8_t* right_first,
+                      const double* verts, const int32_t* nverts, const int32_t* nobs, const double* delta,
+                      const double* limits, double* traj_X, double* traj_U, int32_t* steps, int32_t* goal_steps,
+                      int32_t* status, int64_t* total_solves, void* cuda_stream);
+
+/* FP64 FMA-chain probe used by bench.py to measure the FP64 pipe peak on the box (roofline denominator).
+ * Launches `blocks` x `threads` threads, each running `iters` x 8 independent FMAs; out[blocks*threads]. */
+int ldcbf_probe_fp64_fma(int blocks, int threads, int iters, double* out, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDCBF_MPC_H */
