@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py — LDCBF-MPC QP solves/sec (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one batched MPC step (half-planes K1 + heading/assembly/solve/integrate K2+K3) over the batch of
+BASELINE.json config 2 ("Batched basic simulation: 4096 randomized start/goal poses x 3 obstacles"), one solve per
+scenario, inputs resident in HBM.  Each rank owns its own 4096 scenarios (weak scaling, no data-path collective);
+the time of a step is measured with CUDA events on the launching stream, L2 is flushed between timed steps, and
+the job time is the max over ranks.
+
+Extra keys on the JSON line: `roofline` (dominant kernel, FP64-pipe bound, peak measured live with an FMA-chain
+probe), `roofline_hbm` (half-plane builder vs MEASURED_PEAKS.json), `cpu_baseline` (the numpy oracle port on the
+host cores), `e2e` (host buffers -> H2D -> step -> D2H through BatchedHumanoidMPC.step_host), `p50_step_us`,
+`large_batch` (same step at B = 2^20 where the GPU is full), `clocks`.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "humanoid-navigation-using-mpc-ldcbf_b200"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "ldcbf_mpc_qp_solves_per_sec"
+UNIT = "solves/s"
+N_HORIZON = 3
+WORKLOAD = "config2: batched basic simulation, 4096 randomized start/goal poses x 3 circle obstacles, N=3, T=0.4"
+# algorithmic flop model of the fused step kernel at (N, n_obs) = (3, 3), DESIGN.md §6
+FLOP_PER_ITER = 470.0
+FLOP_SETUP = 500.0
+BYTES_K1 = 984.0        # 16*E + 8*7 + 32*n_obs at E = 52, n_obs = 3
+BYTES_STEP = 1232.0     # inputs 984 B + outputs 248 B
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU legs (oracle port): the only place bench.py executes oracle/
+# ---------------------------------------------------------------------------------------------------------------------
+def _cpu_init():
+    # one BLAS thread per worker process: the port is a scalar loop, oversubscription only slows it down
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    sys.path.insert(0, ROOT)
+
+
+def _cpu_worker(job):
+    from oracle import mpc
+    states, goals, foots, rings = job
+    n = 0
+    for s, g, f, r in zip(states, goals, foots, rings):
+        mpc.mpc_step(s, g, r, [int(v) for v in f], N=N_HORIZON, sampling_time=0.4)
+        n += 1
+    return n
+
+
+class CpuPort:
+    """The numpy oracle (faithful per-step control flow + exact NNLS solve) on `cores` worker processes."""
+
+    def __init__(self, cores):
+        import multiprocessing as mp
+        self.cores = cores
+        self.pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init)
+
+    def rate(self, sc, foots, n_sample):
+        idx = np.arange(n_sample) % len(sc["state"])
+        jobs = [(sc["state"][c], sc["goal"][c], foots[c], [sc["rings"][i] for i in c])
+                for c in np.array_split(idx, self.cores) if len(c)]
+        t0 = time.perf_counter()
+        n = sum(self.pool.map(_cpu_worker, jobs))
+        wall = time.perf_counter() - t0
+        return n / wall, n, wall
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU path for this hot path.  CasADi/IPOPT are not installable offline
+    (SURVEY.md §8c), so this times the oracle port — a numpy restatement of HumanoidMpc.py:380-455 with an exact
+    QP solve — on all host cores, on the same config/metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from ldcbf_b200 import scenarios
+    cores = os.cpu_count() or 1
+    sc = scenarios.config2(512, seed=0)
+    foots = scenarios.foot_window(sc["right_first"], 0, N_HORIZON)
+    per_step = 64 * cores      # bounded sample of the 4096-scenario batch per "step"
+    port = CpuPort(cores)
+    for _ in range(min(args.warmup, 2)):
+        port.rate(sc, foots, per_step)
+    t_total, n_total = 0.0, 0
+    steps = max(1, min(args.steps, 20))
+    for _ in range(steps):
+        _, n, wall = port.rate(sc, foots, per_step)
+        t_total += wall
+        n_total += n
+    port.close()
+    value = n_total / t_total
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_total / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch": args.batch, "horizon": N_HORIZON, "obstacles": 3},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{per_step} scenarios of the batch per step x {steps} steps; numpy oracle "
+                                       "(reference restatement; CasADi/IPOPT unavailable offline)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# clocks sampler
+# ---------------------------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.samples, self.stop, self.index = [], False, index
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append((float(f[0]), float(f[1]), f[2:6]))
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(s[0] for s in self.samples), "sm_max_mhz": self.samples[0][1],
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def timed_steps(fn, steps, flush, torch):
+    """Per-step CUDA-event times (ms) with an L2 flush (write of a > L2 buffer) before every timed step."""
+    ts = []
+    for _ in range(steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return ts
+
+
+def device_inputs(sc, foots, torch, rep=1):
+    def cu(a, dt):
+        a = np.ascontiguousarray(np.tile(a, (rep,) + (1,) * (a.ndim - 1)))
+        return torch.as_tensor(a, dtype=dt).cuda()
+    return dict(x0=cu(sc["state"][:, :4], torch.float64), th=cu(sc["state"][:, 4], torch.float64),
+                goal=cu(sc["goal"], torch.float64), foot=cu(foots, torch.int8), verts=cu(sc["verts"], torch.float64),
+                nverts=cu(sc["nverts"], torch.int32), nobs=cu(sc["nobs"], torch.int32))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import ldcbf_b200 as L
+    from ldcbf_b200 import scenarios
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    # fork the CPU-baseline workers before this process creates a CUDA context
+    port = CpuPort(os.cpu_count() or 1) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L.lib()
+    B, N = args.batch, N_HORIZON
+    sc = scenarios.config2(B, seed=rank)                     # each rank owns its own scenarios (weak scaling)
+    foots = scenarios.foot_window(sc["right_first"], 0, N)
+    d = device_inputs(sc, foots, torch)
+    prm = L.default_params(0.4)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+    out = {}
+
+    def step():
+        L.mpc_step(prm, d["x0"], d["th"], d["goal"], d["foot"], d["verts"], d["nverts"], d["nobs"], out=out)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    sync_all()
+    with Clocks(local) as clk:
+        sync_all()
+        ts = timed_steps(step, args.steps, flush, torch)
+        sync_all()
+        total_ms = torch.tensor([sum(ts)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        total_ms = float(total_ms.item())
+        value = B * args.steps * world / (total_ms * 1e-3)
+        iters = out["iters"].double()
+        status = torch.bincount(out["status"], minlength=4).tolist()
+
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "batch_per_gpu": B, "horizon": N, "obstacles": 3,
+                           "timing": "CUDA events per step, L2 flushed (256 MB write) between timed steps",
+                           "solver": "dual active set (Goldfarb-Idnani) in CoM-position space, fp64"},
+                "p50_step_us": 1e3 * statistics.median(ts), "gpu_launches": 2 * args.steps,
+                "iters_mean": float(iters.mean().item()), "status_counts": status}
+
+        # ---- end to end through the public API with host buffers (every rank; max over ranks)
+        e2e_res = e2e(L, sc, foots, args, torch)
+        e2e_ms = torch.tensor([e2e_res["ms_total"]], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+        e2e_ms = float(e2e_ms.item())
+        line["e2e"] = {"value": B * args.steps * world / (e2e_ms * 1e-3), "unit": UNIT,
+                       "h2d_bytes_per_step": e2e_res["h2d"], "d2h_bytes_per_step": e2e_res["d2h"],
+                       "ms_per_step": e2e_ms / args.steps,
+                       "api": "BatchedHumanoidMPC.step_host (pinned host state in, next state / u0 / obj / status out)"}
+        if rank == 0:
+            # ---- kernel-only timing of the dominant kernel for the roofline (same inputs, L2 flushed)
+            t_qp = timed_steps(lambda: L.mpc_qp(prm, d["x0"], d["th"], d["goal"], d["foot"], out["c_eta"], d["nobs"],
+                                                out=out), min(args.steps, 50), flush, torch)
+            peak_fp64 = max(L.probe_fp64() for _ in range(3))
+            flops = float((iters * FLOP_PER_ITER + FLOP_SETUP).sum().item())
+            ach = flops / (statistics.mean(t_qp) * 1e-3) / 1e12
+            line["roofline"] = {"bound": "fp64", "kernel": "mpc_qp_kernel<3,4>", "achieved": ach, "peak": peak_fp64,
+                                "unit": "TFLOP/s", "frac": ach / peak_fp64, "traffic": profile_traffic(B),
+                                "kernel_ms": statistics.mean(t_qp),
+                                "peak_source": "FP64 FMA-chain probe measured in this run (MEASURED_PEAKS.json has no fp64 entry)",
+                                "note": "B=4096 is 128 warps on 148 SMs: latency-bound by construction; large_batch "
+                                        "shows the same kernel with the GPU full"}
+            # ---- large batch: the regime where the GPU is full
+            line["large_batch"] = large_batch(L, sc, foots, prm, flush, peak_fp64, torch)
+    if rank == 0:
+        line["clocks"] = clk.summary()
+        if port is not None:
+            cores = port.cores
+            n_sample = 256 * cores
+            port.rate(sc, foots, cores * 4)
+            rate, n, wall = port.rate(sc, foots, n_sample)
+            port.close()
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{n} scenarios of the same batch, one MPC step each ({wall:.1f} s); numpy "
+                                              "oracle (reference restatement; CasADi/IPOPT unavailable offline)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def profile_traffic(batch):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if one exists for this batch."""
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "kernel_summary.json")))
+        return prof["mpc_qp_kernel"]["dram_bytes_per_launch"].get(str(batch))
+    except Exception:
+        return None
+
+
+def large_batch(L, sc, foots, prm, flush, peak_fp64, torch, B=1 << 20):
+    rep = B // len(sc["state"])
+    d = device_inputs(sc, foots, torch, rep)
+    Bl = d["x0"].shape[0]
+    out = {}
+    step = lambda: L.mpc_step(prm, d["x0"], d["th"], d["goal"], d["foot"], d["verts"], d["nverts"], d["nobs"], out=out)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    ts = timed_steps(step, 10, flush, torch)
+    # K1 alone ([B,2] positions) and K2+K3 alone
+    p2 = d["x0"][:, [0, 2]].contiguous()
+    t_hp = timed_steps(lambda: L.half_planes(p2, d["verts"], d["nverts"], d["nobs"], c_eta=out["c_eta"]), 10, flush, torch)
+    t_qp = timed_steps(lambda: L.mpc_qp(prm, d["x0"], d["th"], d["goal"], d["foot"], out["c_eta"], d["nobs"], out=out),
+                       10, flush, torch)
+    iters = out["iters"].double()
+    flops = float((iters * FLOP_PER_ITER + FLOP_SETUP).sum().item())
+    ach = flops / (statistics.mean(t_qp) * 1e-3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    gbs_k1 = BYTES_K1 * Bl / (statistics.mean(t_hp) * 1e-3) / 1e9
+    return {"batch": Bl, "value": Bl / (statistics.mean(ts) * 1e-3), "unit": UNIT, "ms_per_step": statistics.mean(ts),
+            "roofline": {"bound": "fp64", "kernel": "mpc_qp_kernel<3,4>", "achieved": ach, "peak": peak_fp64,
+                         "unit": "TFLOP/s", "frac": ach / peak_fp64, "kernel_ms": statistics.mean(t_qp),
+                         "traffic": profile_traffic(Bl)},
+            "roofline_hbm": {"bound": "hbm", "kernel": "halfplane_kernel<32>", "achieved": gbs_k1, "peak": hbm_peak,
+                             "unit": "GB/s", "frac": gbs_k1 / hbm_peak, "kernel_ms": statistics.mean(t_hp),
+                             "peak_source": hbm_src}}
+
+
+def e2e(L, sc, foots, args, torch):
+    eng = L.BatchedHumanoidMPC(sc["goal"], sc["verts"], sc["nverts"], sc["nobs"], N_horizon=N_HORIZON, sampling_time=0.4)
+    state_h = torch.as_tensor(sc["state"], dtype=torch.float64).pin_memory()
+    foot_h = torch.as_tensor(foots, dtype=torch.int8).pin_memory()
+    for _ in range(3):
+        eng.step_host(state_h, foot_h)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        res = eng.step_host(state_h, foot_h)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    assert int((res["status"] == 0).sum()) > 0
+    return {"ms_total": max(e0.elapsed_time(e1), wall * 1e3), "h2d": eng.h2d_bytes_per_step,
+            "d2h": eng.d2h_bytes_per_step}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

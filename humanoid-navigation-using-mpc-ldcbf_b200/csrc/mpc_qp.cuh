@@ -1,5 +1,5 @@
 // K2+K3 device code: heading schedule, QP assembly in CoM-position space and the exact dual active-set
-// solve for ONE scenario, executed by ONE thread with all problem data in registers / thread-local memory.
+// solve for ONE scenario, executed by ONE thread with all problem data in registers.
 //
 // Reference semantics restated (paths relative to the reference root, HumanoidNavigation/):
 //   MPC/HumanoidMpc.py:137-160  heading schedule (current CoM for every k, no angle wrap, theta += omega*Ts)
@@ -19,21 +19,16 @@
 // are exact consequences of x_{k+1} = A x_k + B u_k, the cost becomes ||w - (g,..,g)||^2 (Hessian 2I) and
 // every constraint row is (scalar pattern over k) x (unit 2-vector): the QP is the Euclidean projection of
 // the stacked goal onto a polytope.  It is solved exactly with the Goldfarb-Idnani dual active-set
-// method; with Hessian I the projector onto the active normals is a <= 2N Gram/Cholesky solve rebuilt
-// from scratch every iteration (<= 6x6 here), so there is no factor-update bookkeeping.
+// method.  With Hessian I the step directions need only the Gram matrix of the active normals, kept in
+// 2N fixed slots (inactive slot = zero normal, unit Gram diagonal) so that the 2N x 2N Cholesky, both
+// triangular solves and every update are fully unrolled with static register indices: no local memory,
+// no divergence between the scenarios of a warp other than the iteration count.
 // The maneuverability row k and the longitudinal walking-velocity row k+1 are the same linear form
 // (cos theta_{k+1}, sin theta_{k+1}) . v_{k+1}; they are merged into one row with the tighter upper bound.
 #pragma once
 #include "ldcbf_common.cuh"
 
 namespace ldcbf {
-
-template <int N>
-struct RowScale {
-    // 1/sqrt(4k-3): norm of the velocity-row pattern (1, -2, 2, ..., +-2) over p_k, p_{k-1}, .., p_1
-    __device__ __forceinline__ static double vel(int k) { return rsqrt((double)(4 * k - 3)); }
-    __device__ __forceinline__ static double leg(int k) { return k == 0 ? 1.0 : 0.70710678118654752440; }
-};
 
 // Output of one solve, kept in registers by the caller.
 template <int N>
@@ -46,37 +41,53 @@ struct QpSolution {
     int status, iters;
 };
 
-// Dense signed normal (length 2N) of candidate row `id`, with sign sg (+1: a.w >= lo, -1: -a.w >= -hi).
+// Row identifiers: leg(k,sub) = 2k+sub (k<N); vel(k,sub) = 2N + 2(k-1) + sub (k=1..N);
+// cbf(k,o) = 4N + (k-1)*MO + o (k=1..N).  A candidate is (id, sg): sg=+1 means a.w >= lo, -1 means -a.w >= -hi.
+//
+// Dense signed normal in p-space, a[2i], a[2i+1] = coefficient on p_{i+1}:
+//   leg(k):  +r on p_{k+1}, -r on p_k                      r = (c_k, s_k) or (-s_k, c_k)
+//   vel(k):  gtil r on p_k, -+2 gtil r on p_{k-1}, ..      r = (c_k, s_k) or (-s_k, foot_k c_k)
+//   cbf(k):  eta_o on p_k
 template <int N, int MO>
-__device__ __forceinline__ void row_normal(int id, double sg, const double* rc, const double* rs, const int* ft,
-                                           const double* ex, const double* ey, double* a) {
+__device__ __forceinline__ void row_normal(int id, double sg, double gtil, const double (&rc)[N + 1],
+                                           const double (&rs)[N + 1], const int (&ft)[N + 1],
+                                           const double (&ex)[MO], const double (&ey)[MO], double (&a)[2 * N]) {
+    // decode without dynamic register indexing: select chains over the (static) k and o
+    int typ, k, sub;   // typ 0 leg, 1 vel, 2 cbf; k = state index the row "ends" at (1..N)
+    if (id < 2 * N) { typ = 0; k = (id >> 1) + 1; sub = id & 1; }
+    else if (id < 4 * N) { typ = 1; k = ((id - 2 * N) >> 1) + 1; sub = id & 1; }
+    else { typ = 2; k = (id - 4 * N) / MO + 1; sub = (id - 4 * N) - (k - 1) * MO; }
+    const int kth = (typ == 0) ? k - 1 : k;     // heading index used by the row
+    double c = 0.0, s = 0.0, f = 1.0;
 #pragma unroll
-    for (int i = 0; i < 2 * N; ++i) a[i] = 0.0;
-    if (id < 2 * N) {                       // leg reachability (k, sub): r.(p_{k+1} - p_k)
-        const int k = id >> 1, sub = id & 1;
-        const double s = sg * RowScale<N>::leg(k);
-        const double rx = (sub ? -rs[k] : rc[k]) * s, ry = (sub ? rc[k] : rs[k]) * s;
-        a[2 * k] = rx; a[2 * k + 1] = ry;
-        if (k > 0) { a[2 * k - 2] = -rx; a[2 * k - 1] = -ry; }
-    } else if (id < 4 * N) {                // velocity rows at state k = 1..N: r.v_k / (gtil sqrt(4k-3))
-        const int j = id - 2 * N, k = (j >> 1) + 1, sub = j & 1;
-        const double s = sg * RowScale<N>::vel(k);
-        const double rx = (sub ? -rs[k] : rc[k]) * s, ry = (sub ? (double)ft[k] * rc[k] : rs[k]) * s;
-        a[2 * (k - 1)] = rx; a[2 * (k - 1) + 1] = ry;
-        double alt = -2.0;
-        for (int i = k - 1; i >= 1; --i) { a[2 * (i - 1)] = alt * rx; a[2 * (i - 1) + 1] = alt * ry; alt = -alt; }
-    } else {                                // LDCBF (k, o): eta_o . p_k
-        const int j = id - 4 * N, k = j / MO + 1, o = j - (k - 1) * MO;
-        a[2 * (k - 1)] = sg * ex[o]; a[2 * (k - 1) + 1] = sg * ey[o];
+    for (int j = 0; j <= N; ++j) if (j == kth) { c = rc[j]; s = rs[j]; f = (double)ft[j]; }
+    double rx, ry;
+    if (typ == 2) {
+        rx = 0.0; ry = 0.0;
+#pragma unroll
+        for (int o = 0; o < MO; ++o) if (o == sub) { rx = ex[o]; ry = ey[o]; }
+    } else if (sub == 0) { rx = c; ry = s; }
+    else { rx = -s; ry = (typ == 1) ? f * c : c; }
+    rx *= sg; ry *= sg;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {               // coefficient pattern on p_{i+1}
+        const int d = k - 1 - i;                // 0 on the row's own state
+        double kap = 0.0;
+        if (d == 0) kap = (typ == 1) ? gtil : 1.0;
+        else if (d > 0) {
+            if (typ == 0) kap = (d == 1) ? -1.0 : 0.0;
+            else if (typ == 1) kap = (d & 1) ? -2.0 * gtil : 2.0 * gtil;
+        }
+        a[2 * i] = kap * rx; a[2 * i + 1] = kap * ry;
     }
 }
 
-// One scenario.  c_eta points at this scenario's [max_obs][4] block (c_x, c_y, eta_x, eta_y).
+// One scenario.  ce[o] = (c_x, c_y, eta_x, eta_y) for o < nb.
 template <int N, int MO>
-__device__ void solve_scenario(const StepConst& C, double p0x, double v0x, double p0y, double v0y, double th0,
-                               double gx, double gy, const int* ft /*[N+1]*/, const double4* c_eta, int nb,
-                               double delta, double alpha_over_pi, double vmax0, double omega_max,
-                               double omega_min, QpSolution<N>& S) {
+__device__ __forceinline__ void solve_scenario(const StepConst& C, double p0x, double v0x, double p0y, double v0y,
+                                               double th0, double gx, double gy, const int (&ft)[N + 1],
+                                               const double4 (&ce)[MO], int nb, double delta, double alpha_over_pi,
+                                               double vmax0, double omega_max, double omega_min, QpSolution<N>& S) {
     constexpr int NV = 2 * N;
     double rc[N + 1], rs[N + 1];
     // ---- heading schedule (HumanoidMpc.py:137-160)
@@ -101,34 +112,38 @@ __device__ void solve_scenario(const StepConst& C, double p0x, double v0x, doubl
     for (int o = 0; o < MO; ++o) {
         ex[o] = 0.0; ey[o] = 0.0; hb[o] = -1.0;
         if (o < nb) {
-            const double4 ce = c_eta[o];
-            ex[o] = ce.z; ey[o] = ce.w;
-            hb[o] = ce.z * ce.x + ce.w * ce.y + delta;
-            if (!(ce.z == ce.z) || !(ce.w == ce.w)) status = LDCBF_STATUS_DEGENERATE;
+            ex[o] = ce[o].z; ey[o] = ce[o].w;
+            hb[o] = ce[o].z * ce[o].x + ce[o].w * ce[o].y + delta;
+            if (!(ex[o] == ex[o]) || !(ey[o] == ey[o])) status = LDCBF_STATUS_DEGENERATE;
             // constant k = 0 row (HumanoidMpc.py:284-292 with k = 0)
-            else if (ce.z * p0x + ce.w * p0y - hb[o] < -C.eps_const_row) status = LDCBF_STATUS_INFEASIBLE;
+            else if (ex[o] * p0x + ey[o] * p0y - hb[o] < -C.eps_const_row) status = LDCBF_STATUS_INFEASIBLE;
         }
     }
-    // ---- row bounds (normalised)
     double vhi[N + 1];
+    vhi[0] = 0.0;
 #pragma unroll
     for (int k = 1; k <= N; ++k) vhi[k] = fmin(vmax0, vmax0 - alpha_over_pi * fabs(S.om[k - 1]));
 
-    // ---- Goldfarb-Idnani dual active set on  min ||w - g||^2  s.t. rows
+    // ---- Goldfarb-Idnani dual active set on  min 1/2 ||w - g||^2  s.t. rows
     double px[N + 1], py[N + 1];
     px[0] = p0x; py[0] = p0y;
 #pragma unroll
     for (int k = 1; k <= N; ++k) { px[k] = gx; py[k] = gy; }   // unconstrained optimum
 
-    int na = 0;
-    int aid[NV];
-    double asg[NV], u[NV];
-    double An[NV][NV];      // signed normals of the active rows
+    unsigned amask = 0;            // occupied slots
+    double An[NV][NV];             // signed normals per slot (zero when free)
+    double u[NV];                  // multipliers per slot
+    double G[NV][NV];              // Gram matrix of the slots, lower triangle; identity on free slots
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        u[j] = 0.0;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) { An[j][i] = 0.0; G[j][i] = (i == j) ? 1.0 : 0.0; }
+    }
     int iters = 0;
-    const double inv_gtil = 1.0 / C.gtil;
 
     while (status == LDCBF_STATUS_SOLVED) {
-        // -- most violated row at the current point
+        // -- most violated row at the current point (natural units: m, m/s)
         double best = -C.eps_active, bsg = 0.0;
         int bid = -1;
         {
@@ -136,24 +151,22 @@ __device__ void solve_scenario(const StepConst& C, double p0x, double v0x, doubl
 #pragma unroll
             for (int k = 0; k < N; ++k) {
                 const double dx = px[k + 1] - px[k], dy = py[k + 1] - py[k];
-                const double il = RowScale<N>::leg(k);
-                const double lg = (rc[k] * dx + rs[k] * dy) * il;
-                const double lt = (rc[k] * dy - rs[k] * dx) * il;
+                const double lg = rc[k] * dx + rs[k] * dy;
+                const double lt = rc[k] * dy - rs[k] * dx;
                 const double off = (double)ft[k] * C.foot_offset;
                 double s;
-                s = lg - C.l_min_x * il;          if (s < best) { best = s; bid = 2 * k; bsg = 1.0; }
-                s = C.l_max_x * il - lg;          if (s < best) { best = s; bid = 2 * k; bsg = -1.0; }
-                s = lt - (C.l_min_y - off) * il;  if (s < best) { best = s; bid = 2 * k + 1; bsg = 1.0; }
-                s = (C.l_max_y - off) * il - lt;  if (s < best) { best = s; bid = 2 * k + 1; bsg = -1.0; }
+                s = lg - C.l_min_x;          if (s < best) { best = s; bid = 2 * k; bsg = 1.0; }
+                s = C.l_max_x - lg;          if (s < best) { best = s; bid = 2 * k; bsg = -1.0; }
+                s = lt - (C.l_min_y - off);  if (s < best) { best = s; bid = 2 * k + 1; bsg = 1.0; }
+                s = (C.l_max_y - off) - lt;  if (s < best) { best = s; bid = 2 * k + 1; bsg = -1.0; }
                 Vx = C.gtil * dx - Vx; Vy = C.gtil * dy - Vy;       // v_{k+1}
                 const int kk = k + 1;
-                const double iv = RowScale<N>::vel(kk) * inv_gtil;
-                const double vl = (rc[kk] * Vx + rs[kk] * Vy) * iv;
-                const double vt = ((double)ft[kk] * rc[kk] * Vy - rs[kk] * Vx) * iv;
-                s = vl - C.v_min0 * iv;           if (s < best) { best = s; bid = 2 * N + 2 * k; bsg = 1.0; }
-                s = vhi[kk] * iv - vl;            if (s < best) { best = s; bid = 2 * N + 2 * k; bsg = -1.0; }
-                s = vt - C.v_min1 * iv;           if (s < best) { best = s; bid = 2 * N + 2 * k + 1; bsg = 1.0; }
-                s = C.v_max1 * iv - vt;           if (s < best) { best = s; bid = 2 * N + 2 * k + 1; bsg = -1.0; }
+                const double vl = rc[kk] * Vx + rs[kk] * Vy;
+                const double vt = (double)ft[kk] * rc[kk] * Vy - rs[kk] * Vx;
+                s = vl - C.v_min0;           if (s < best) { best = s; bid = 2 * N + 2 * k; bsg = 1.0; }
+                s = vhi[kk] - vl;            if (s < best) { best = s; bid = 2 * N + 2 * k; bsg = -1.0; }
+                s = vt - C.v_min1;           if (s < best) { best = s; bid = 2 * N + 2 * k + 1; bsg = 1.0; }
+                s = C.v_max1 - vt;           if (s < best) { best = s; bid = 2 * N + 2 * k + 1; bsg = -1.0; }
 #pragma unroll
                 for (int o = 0; o < MO; ++o) {
                     if (o < nb) {
@@ -166,66 +179,69 @@ __device__ void solve_scenario(const StepConst& C, double p0x, double v0x, doubl
         if (bid < 0) break;   // primal feasible: optimal
 
         double np[NV];
-        row_normal<N, MO>(bid, bsg, rc, rs, ft, ex, ey, np);
+        row_normal<N, MO>(bid, bsg, C.gtil, rc, rs, ft, ex, ey, np);
+        double nn = 0.0;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) nn += np[i] * np[i];
         double s_p = best, u_p = 0.0;
         // -- add row p: partial steps until it can enter the active set
         for (;;) {
             if (++iters > C.max_iter) { status = LDCBF_STATUS_MAX_ITER; break; }
-            // r = (N^T N)^-1 N^T n+ ,  z = n+ - N r
-            double r[NV], z[NV];
+            // d = N^T n+ ;  r = (N^T N)^-1 d ;  z = n+ - N r
+            double d[NV], r[NV], L[NV][NV];
 #pragma unroll
-            for (int i = 0; i < NV; ++i) z[i] = np[i];
-            if (na > 0) {
-                double G[NV][NV], d[NV];
-                for (int j = 0; j < na; ++j) {
-                    double acc = 0.0;
+            for (int j = 0; j < NV; ++j) {
+                double acc = 0.0;
 #pragma unroll
-                    for (int i = 0; i < NV; ++i) acc += An[j][i] * np[i];
-                    d[j] = acc;
-                    for (int l = 0; l <= j; ++l) {
-                        double g = 0.0;
+                for (int i = 0; i < NV; ++i) acc += An[j][i] * np[i];
+                d[j] = acc;
+            }
+            // Cholesky G = L L^T (full 2N x 2N, static), inverse diagonal kept in L[j][j]
 #pragma unroll
-                        for (int i = 0; i < NV; ++i) g += An[j][i] * An[l][i];
-                        G[j][l] = g;
-                    }
-                }
-                // Cholesky G = L L^T in place (lower), then two triangular solves
-                for (int j = 0; j < na; ++j) {
-                    double dj = G[j][j];
-                    for (int l = 0; l < j; ++l) dj -= G[j][l] * G[j][l];
-                    dj = sqrt(fmax(dj, 1e-300));
-                    G[j][j] = dj;
-                    const double inv = 1.0 / dj;
-                    for (int i = j + 1; i < na; ++i) {
-                        double v = G[i][j];
-                        for (int l = 0; l < j; ++l) v -= G[i][l] * G[j][l];
-                        G[i][j] = v * inv;
-                    }
-                }
-                for (int j = 0; j < na; ++j) {
-                    double v = d[j];
-                    for (int l = 0; l < j; ++l) v -= G[j][l] * r[l];
-                    r[j] = v / G[j][j];
-                }
-                for (int j = na - 1; j >= 0; --j) {
-                    double v = r[j];
-                    for (int l = j + 1; l < na; ++l) v -= G[l][j] * r[l];
-                    r[j] = v / G[j][j];
-                }
-                for (int j = 0; j < na; ++j) {
+            for (int j = 0; j < NV; ++j) {
+                double dj = G[j][j];
 #pragma unroll
-                    for (int i = 0; i < NV; ++i) z[i] -= r[j] * An[j][i];
+                for (int l = 0; l < j; ++l) dj -= L[j][l] * L[j][l];
+                const double inv = rsqrt(fmax(dj, 1e-300));
+                L[j][j] = inv;
+#pragma unroll
+                for (int i = j + 1; i < NV; ++i) {
+                    double v = G[i][j];
+#pragma unroll
+                    for (int l = 0; l < j; ++l) v -= L[i][l] * L[j][l];
+                    L[i][j] = v * inv;
                 }
             }
-            double zz = 0.0;
 #pragma unroll
-            for (int i = 0; i < NV; ++i) zz += z[i] * z[i];
-            const bool dependent = !(zz > 1e-14) || na >= NV;
+            for (int j = 0; j < NV; ++j) {
+                double v = d[j];
+#pragma unroll
+                for (int l = 0; l < j; ++l) v -= L[j][l] * r[l];
+                r[j] = v * L[j][j];
+            }
+#pragma unroll
+            for (int j = NV - 1; j >= 0; --j) {
+                double v = r[j];
+#pragma unroll
+                for (int l = j + 1; l < NV; ++l) v -= L[l][j] * r[l];
+                r[j] = v * L[j][j];
+            }
+            double z[NV], zz = 0.0;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                double v = np[i];
+#pragma unroll
+                for (int j = 0; j < NV; ++j) v -= r[j] * An[j][i];
+                z[i] = v;
+                zz += v * v;
+            }
+            const bool dependent = !(zz > 1e-13 * nn) || amask == (1u << NV) - 1u;
             // dual step length: largest t keeping the active multipliers non-negative
             double t1 = INFINITY;
             int ldrop = -1;
-            for (int j = 0; j < na; ++j) {
-                if (r[j] > 1e-14) {
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                if (((amask >> j) & 1u) && r[j] > 1e-13) {
                     const double tj = u[j] / r[j];
                     if (tj < t1) { t1 = tj; ldrop = j; }
                 }
@@ -233,30 +249,51 @@ __device__ void solve_scenario(const StepConst& C, double p0x, double v0x, doubl
             const double t2 = dependent ? INFINITY : -s_p / zz;
             const double t = fmin(t1, t2);
             if (!(t < INFINITY)) { status = LDCBF_STATUS_INFEASIBLE; break; }
-            for (int j = 0; j < na; ++j) u[j] -= t * r[j];
+#pragma unroll
+            for (int j = 0; j < NV; ++j) u[j] -= t * r[j];
             u_p += t;
             if (!dependent) {
 #pragma unroll
                 for (int k = 1; k <= N; ++k) { px[k] += t * z[2 * (k - 1)]; py[k] += t * z[2 * (k - 1) + 1]; }
                 s_p += t * zz;
             }
-            if (t2 <= t1) {          // full step: row p becomes active
-                aid[na] = bid; asg[na] = bsg; u[na] = u_p;
+            if (t2 <= t1) {          // full step: row p enters the first free slot
+                const int slot = __ffs(~amask) - 1;
 #pragma unroll
-                for (int i = 0; i < NV; ++i) An[na][i] = np[i];
-                ++na;
+                for (int j = 0; j < NV; ++j) {
+                    if (j == slot) {
+                        u[j] = u_p;
+#pragma unroll
+                        for (int i = 0; i < NV; ++i) An[j][i] = np[i];
+#pragma unroll
+                        for (int l = 0; l < NV; ++l) {
+                            if (l < j) G[j][l] = d[l];
+                            else if (l > j) G[l][j] = d[l];
+                        }
+                        G[j][j] = nn;
+                    }
+                }
+                amask |= 1u << slot;
                 break;
             }
-            // partial step: drop row ldrop and try again
-            for (int j = ldrop; j < na - 1; ++j) {
-                aid[j] = aid[j + 1]; asg[j] = asg[j + 1]; u[j] = u[j + 1];
+            // partial step: free slot ldrop and try again
 #pragma unroll
-                for (int i = 0; i < NV; ++i) An[j][i] = An[j + 1][i];
+            for (int j = 0; j < NV; ++j) {
+                if (j == ldrop) {
+                    u[j] = 0.0;
+#pragma unroll
+                    for (int i = 0; i < NV; ++i) An[j][i] = 0.0;
+#pragma unroll
+                    for (int l = 0; l < NV; ++l) {
+                        if (l < j) G[j][l] = 0.0;
+                        else if (l > j) G[l][j] = 0.0;
+                    }
+                    G[j][j] = 1.0;
+                }
             }
-            --na;
+            amask &= ~(1u << ldrop);
         }
     }
-    (void)aid; (void)asg;
 
     // ---- outputs: states, footsteps, objective
     S.status = status;

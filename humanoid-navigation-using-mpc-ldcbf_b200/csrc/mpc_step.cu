@@ -57,9 +57,12 @@ __global__ void __launch_bounds__(128) mpc_qp_kernel(StepConst C, int B, int max
     double aop, vmax0, omax, omin;
     load_limits(C, io.limits, b, aop, vmax0, omax, omin);
     const int nb = min(io.nobs[b], MO);
+    double4 ce[MO];
+    const double4* gce = reinterpret_cast<const double4*>(io.c_eta) + (size_t)b * max_obs;
+#pragma unroll
+    for (int o = 0; o < MO; ++o) ce[o] = (o < nb) ? gce[o] : make_double4(0.0, 0.0, 0.0, 0.0);
     QpSolution<N> S;
-    solve_scenario<N, MO>(C, x.x, x.y, x.z, x.w, io.theta0[b], g.x, g.y, ft,
-                          reinterpret_cast<const double4*>(io.c_eta) + (size_t)b * max_obs, nb,
+    solve_scenario<N, MO>(C, x.x, x.y, x.z, x.w, io.theta0[b], g.x, g.y, ft, ce, nb,
                           io.delta ? io.delta[b] : 0.0, aop, vmax0, omax, omin, S);
     store_solution<N>(S, b, io.U, io.X, io.theta, io.omega, io.obj, io.status, io.iters);
 }

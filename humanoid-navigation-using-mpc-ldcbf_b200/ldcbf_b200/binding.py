@@ -9,6 +9,8 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libldcbf_b200.so")
 
+MAX_OBSTACLES = 8      # LDCBF_MAX_OBSTACLES of include/ldcbf_mpc.h
+
 EXPORTS = ("ldcbf_abi_version", "ldcbf_params_default", "ldcbf_last_cuda_error", "ldcbf_workspace_bytes",
            "ldcbf_halfplanes_f64", "ldcbf_mpc_qp_f64", "ldcbf_mpc_step_f64", "ldcbf_lidar_cast_f64",
            "ldcbf_rollout_f64", "ldcbf_probe_fp64_fma")
