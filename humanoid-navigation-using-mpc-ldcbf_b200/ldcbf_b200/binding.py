@@ -126,7 +126,7 @@ def half_planes(pos, verts, nverts, nobs, c_eta=None):
 
 
 def _alloc_step_out(B, N, dev, out):
-    out = out or {}
+    out = {} if out is None else out
     def get(name, shape, dt):
         t = out.get(name)
         if t is None:
