@@ -54,6 +54,6 @@ inline int check_launch() {
 // ([B,2] positions: (2,1); [B,4] states: (4,2); [B,5] states with heading: (5,2)).
 int launch_halfplanes(int B, int max_obs, int max_verts, const double* pos, int pos_stride, int y_off,
                       const double* verts, const int32_t* nverts, const int32_t* nobs, double* c_eta,
-                      void* cuda_stream);
+                      bool fast_geometry, void* cuda_stream);
 
 }  // namespace ldcbf

@@ -20,15 +20,54 @@
 // every constraint row is (scalar pattern over k) x (unit 2-vector): the QP is the Euclidean projection of
 // the stacked goal onto a polytope.  It is solved exactly with the Goldfarb-Idnani dual active-set
 // method.  With Hessian I the step directions need only the Gram matrix of the active normals, kept in
-// 2N fixed slots (inactive slot = zero normal, unit Gram diagonal) so that the 2N x 2N Cholesky, both
-// triangular solves and every update are fully unrolled with static register indices: no local memory,
-// no divergence between the scenarios of a warp other than the iteration count.
+// 2N fixed slots (free slot = zero normal, unit diagonal) so that the 2N x 2N Cholesky, both triangular
+// solves and every update are fully unrolled with static register indices: no local memory, and the
+// scenarios of a warp diverge only in their iteration count.
 // The maneuverability row k and the longitudinal walking-velocity row k+1 are the same linear form
 // (cos theta_{k+1}, sin theta_{k+1}) . v_{k+1}; they are merged into one row with the tighter upper bound.
 #pragma once
 #include "ldcbf_common.cuh"
 
 namespace ldcbf {
+
+// The solver source also compiles for the host (tests/cpu_harness builds it into a test-only library so the
+// algorithm is exercised by the CPU test suite); the product library only ever launches it on the device.
+#define LDCBF_HD __host__ __device__ __forceinline__
+LDCBF_HD double add_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    volatile double r = a + b; return r;
+#endif
+}
+LDCBF_HD double mul_rn(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    volatile double r = a * b; return r;
+#endif
+}
+LDCBF_HD double rsqrt_f64(double x) {
+#ifdef __CUDA_ARCH__
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+LDCBF_HD int first_free_slot(unsigned amask) {
+#ifdef __CUDA_ARCH__
+    return __ffs(~amask) - 1;
+#else
+    return __builtin_ffs((int)~amask) - 1;
+#endif
+}
+LDCBF_HD double quiet_nan() {
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double(0x7ff8000000000000LL);
+#else
+    return NAN;
+#endif
+}
 
 // Output of one solve, kept in registers by the caller.
 template <int N>
@@ -49,7 +88,7 @@ struct QpSolution {
 //   vel(k):  gtil r on p_k, -+2 gtil r on p_{k-1}, ..      r = (c_k, s_k) or (-s_k, foot_k c_k)
 //   cbf(k):  eta_o on p_k
 template <int N, int MO>
-__device__ __forceinline__ void row_normal(int id, double sg, double gtil, const double (&rc)[N + 1],
+LDCBF_HD void row_normal(int id, double sg, double gtil, const double (&rc)[N + 1],
                                            const double (&rs)[N + 1], const int (&ft)[N + 1],
                                            const double (&ex)[MO], const double (&ey)[MO], double (&a)[2 * N]) {
     // decode without dynamic register indexing: select chains over the (static) k and o
@@ -84,7 +123,7 @@ __device__ __forceinline__ void row_normal(int id, double sg, double gtil, const
 
 // One scenario.  ce[o] = (c_x, c_y, eta_x, eta_y) for o < nb.
 template <int N, int MO>
-__device__ __forceinline__ void solve_scenario(const StepConst& C, double p0x, double v0x, double p0y, double v0y,
+LDCBF_HD void solve_scenario(const StepConst& C, double p0x, double v0x, double p0y, double v0y,
                                                double th0, double gx, double gy, const int (&ft)[N + 1],
                                                const double4 (&ce)[MO], int nb, double delta, double alpha_over_pi,
                                                double vmax0, double omega_max, double omega_min, QpSolution<N>& S) {
@@ -100,7 +139,7 @@ __device__ __forceinline__ void solve_scenario(const StepConst& C, double p0x, d
         for (int k = 0; k < N; ++k) {
             const double w = fmin(fmax(phi - thk, omega_min), omega_max);
             S.om[k] = w;
-            thk = __dadd_rn(thk, __dmul_rn(w, C.sampling_time));
+            thk = add_rn(thk, mul_rn(w, C.sampling_time));
             S.th[k + 1] = thk;
             sincos(thk, &rs[k + 1], &rc[k + 1]);
         }
@@ -125,15 +164,23 @@ __device__ __forceinline__ void solve_scenario(const StepConst& C, double p0x, d
     for (int k = 1; k <= N; ++k) vhi[k] = fmin(vmax0, vmax0 - alpha_over_pi * fabs(S.om[k - 1]));
 
     // ---- Goldfarb-Idnani dual active set on  min 1/2 ||w - g||^2  s.t. rows
+    //
+    // Active normals live in NV fixed slots (free slot: zero normal).  G is the slots' Gram matrix (identity on
+    // free slots), updated in place when a row enters or leaves; each step factorises it from scratch (a fully
+    // unrolled NV x NV Cholesky): r = G^-1 (N^T n+), z = n+ - N r.  Updating the inverse instead (one rank-1
+    // update per add / drop) was measured 30 % faster but loses the active set on ill-conditioned vertices
+    // (two nearly anti-parallel velocity rows, multipliers ~3e4): a false "infeasible" in 1 of 4096 scenarios.
+    // One loop, one step per trip: every lane of the warp runs the same instruction stream and lanes differ
+    // only in how many trips they need.
     double px[N + 1], py[N + 1];
     px[0] = p0x; py[0] = p0y;
 #pragma unroll
     for (int k = 1; k <= N; ++k) { px[k] = gx; py[k] = gy; }   // unconstrained optimum
 
     unsigned amask = 0;            // occupied slots
-    double An[NV][NV];             // signed normals per slot (zero when free)
+    double An[NV][NV];             // signed normals per slot
     double u[NV];                  // multipliers per slot
-    double G[NV][NV];              // Gram matrix of the slots, lower triangle; identity on free slots
+    double G[NV][NV];              // Gram matrix of the slots, lower triangle (i >= j)
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         u[j] = 0.0;
@@ -141,12 +188,16 @@ __device__ __forceinline__ void solve_scenario(const StepConst& C, double p0x, d
         for (int i = 0; i < NV; ++i) { An[j][i] = 0.0; G[j][i] = (i == j) ? 1.0 : 0.0; }
     }
     int iters = 0;
+    bool need_scan = true;
+    double np[NV], nn = 1.0, s_p = 0.0, u_p = 0.0;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) np[i] = 0.0;
 
     while (status == LDCBF_STATUS_SOLVED) {
-        // -- most violated row at the current point (natural units: m, m/s)
-        double best = -C.eps_active, bsg = 0.0;
-        int bid = -1;
-        {
+        if (need_scan) {
+            // -- most violated row at the current point (natural units: m, m/s)
+            double best = -C.eps_active, bsg = 0.0;
+            int bid = -1;
             double Vx = v0x, Vy = v0y;
 #pragma unroll
             for (int k = 0; k < N; ++k) {
@@ -175,34 +226,33 @@ __device__ __forceinline__ void solve_scenario(const StepConst& C, double p0x, d
                     }
                 }
             }
+            if (bid < 0) break;   // primal feasible: optimal
+            row_normal<N, MO>(bid, bsg, C.gtil, rc, rs, ft, ex, ey, np);
+            nn = 0.0;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) nn += np[i] * np[i];
+            s_p = best; u_p = 0.0;
+            need_scan = false;
         }
-        if (bid < 0) break;   // primal feasible: optimal
+        if (++iters > C.max_iter) { status = LDCBF_STATUS_MAX_ITER; break; }
 
-        double np[NV];
-        row_normal<N, MO>(bid, bsg, C.gtil, rc, rs, ft, ex, ey, np);
-        double nn = 0.0;
+        // d = N^T n+ ;  r = G^-1 d ;  z = n+ - N r
+        double d[NV], r[NV], z[NV], zz = 0.0;
 #pragma unroll
-        for (int i = 0; i < NV; ++i) nn += np[i] * np[i];
-        double s_p = best, u_p = 0.0;
-        // -- add row p: partial steps until it can enter the active set
-        for (;;) {
-            if (++iters > C.max_iter) { status = LDCBF_STATUS_MAX_ITER; break; }
-            // d = N^T n+ ;  r = (N^T N)^-1 d ;  z = n+ - N r
-            double d[NV], r[NV], L[NV][NV];
+        for (int j = 0; j < NV; ++j) {
+            double acc = 0.0;
 #pragma unroll
-            for (int j = 0; j < NV; ++j) {
-                double acc = 0.0;
-#pragma unroll
-                for (int i = 0; i < NV; ++i) acc += An[j][i] * np[i];
-                d[j] = acc;
-            }
-            // Cholesky G = L L^T (full 2N x 2N, static), inverse diagonal kept in L[j][j]
+            for (int i = 0; i < NV; ++i) acc += An[j][i] * np[i];
+            d[j] = acc;
+        }
+        {
+            double L[NV][NV];      // Cholesky factor, inverse diagonal kept in L[j][j]
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
                 double dj = G[j][j];
 #pragma unroll
                 for (int l = 0; l < j; ++l) dj -= L[j][l] * L[j][l];
-                const double inv = rsqrt(fmax(dj, 1e-300));
+                const double inv = rsqrt_f64(fmax(dj, 1e-300));
                 L[j][j] = inv;
 #pragma unroll
                 for (int i = j + 1; i < NV; ++i) {
@@ -226,79 +276,62 @@ __device__ __forceinline__ void solve_scenario(const StepConst& C, double p0x, d
                 for (int l = j + 1; l < NV; ++l) v -= L[l][j] * r[l];
                 r[j] = v * L[j][j];
             }
-            double z[NV], zz = 0.0;
+        }
 #pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                double v = np[i];
+        for (int i = 0; i < NV; ++i) {
+            double v = np[i];
 #pragma unroll
-                for (int j = 0; j < NV; ++j) v -= r[j] * An[j][i];
-                z[i] = v;
-                zz += v * v;
+            for (int j = 0; j < NV; ++j) v -= r[j] * An[j][i];
+            z[i] = v;
+            zz += v * v;
+        }
+        const bool dependent = !(zz > 1e-13 * nn) || amask == (1u << NV) - 1u;
+        // dual step length t1 = min u_j / r_j over r_j > 0, compared by cross-multiplication
+        double t1n = 1.0, t1d = 0.0;          // t1 = t1n / t1d, "infinite" while t1d == 0
+        int ldrop = -1;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            if (((amask >> j) & 1u) && r[j] > 1e-13) {
+                if (ldrop < 0 || u[j] * t1d < t1n * r[j]) { t1n = u[j]; t1d = r[j]; ldrop = j; }
             }
-            const bool dependent = !(zz > 1e-13 * nn) || amask == (1u << NV) - 1u;
-            // dual step length: largest t keeping the active multipliers non-negative
-            double t1 = INFINITY;
-            int ldrop = -1;
+        }
+        // full step t2 = -s_p / zz
+        const bool full = !dependent && (ldrop < 0 || (-s_p) * t1d <= t1n * zz);
+        if (!full && ldrop < 0) { status = LDCBF_STATUS_INFEASIBLE; break; }
+        const double t = full ? (-s_p) / zz : t1n / t1d;
 #pragma unroll
-            for (int j = 0; j < NV; ++j) {
-                if (((amask >> j) & 1u) && r[j] > 1e-13) {
-                    const double tj = u[j] / r[j];
-                    if (tj < t1) { t1 = tj; ldrop = j; }
+        for (int j = 0; j < NV; ++j) u[j] -= t * r[j];
+        u_p += t;
+        if (!dependent) {
+#pragma unroll
+            for (int k = 1; k <= N; ++k) { px[k] += t * z[2 * (k - 1)]; py[k] += t * z[2 * (k - 1) + 1]; }
+            s_p += t * zz;
+        }
+        // -- slot bookkeeping: row p enters the first free slot (full step) or slot ldrop leaves (partial step)
+        const int slot = full ? first_free_slot(amask) : ldrop;
+        if (full) { amask |= 1u << slot; need_scan = true; }
+        else amask &= ~(1u << slot);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            if (j == slot) {
+                u[j] = full ? u_p : 0.0;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) An[j][i] = full ? np[i] : 0.0;
+#pragma unroll
+                for (int l = 0; l < NV; ++l) {
+                    const double val = full ? d[l] : 0.0;
+                    if (l < j) G[j][l] = val;
+                    else if (l > j) G[l][j] = val;
                 }
+                G[j][j] = full ? nn : 1.0;
             }
-            const double t2 = dependent ? INFINITY : -s_p / zz;
-            const double t = fmin(t1, t2);
-            if (!(t < INFINITY)) { status = LDCBF_STATUS_INFEASIBLE; break; }
-#pragma unroll
-            for (int j = 0; j < NV; ++j) u[j] -= t * r[j];
-            u_p += t;
-            if (!dependent) {
-#pragma unroll
-                for (int k = 1; k <= N; ++k) { px[k] += t * z[2 * (k - 1)]; py[k] += t * z[2 * (k - 1) + 1]; }
-                s_p += t * zz;
-            }
-            if (t2 <= t1) {          // full step: row p enters the first free slot
-                const int slot = __ffs(~amask) - 1;
-#pragma unroll
-                for (int j = 0; j < NV; ++j) {
-                    if (j == slot) {
-                        u[j] = u_p;
-#pragma unroll
-                        for (int i = 0; i < NV; ++i) An[j][i] = np[i];
-#pragma unroll
-                        for (int l = 0; l < NV; ++l) {
-                            if (l < j) G[j][l] = d[l];
-                            else if (l > j) G[l][j] = d[l];
-                        }
-                        G[j][j] = nn;
-                    }
-                }
-                amask |= 1u << slot;
-                break;
-            }
-            // partial step: free slot ldrop and try again
-#pragma unroll
-            for (int j = 0; j < NV; ++j) {
-                if (j == ldrop) {
-                    u[j] = 0.0;
-#pragma unroll
-                    for (int i = 0; i < NV; ++i) An[j][i] = 0.0;
-#pragma unroll
-                    for (int l = 0; l < NV; ++l) {
-                        if (l < j) G[j][l] = 0.0;
-                        else if (l > j) G[l][j] = 0.0;
-                    }
-                    G[j][j] = 1.0;
-                }
-            }
-            amask &= ~(1u << ldrop);
         }
     }
 
     // ---- outputs: states, footsteps, objective
     S.status = status;
     S.iters = iters;
-    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const double nan = quiet_nan();
     S.px[0] = p0x; S.py[0] = p0y; S.vx[0] = v0x; S.vy[0] = v0y;
     double obj = (p0x - gx) * (p0x - gx) + (p0y - gy) * (p0y - gy);
     const bool ok = status == LDCBF_STATUS_SOLVED;

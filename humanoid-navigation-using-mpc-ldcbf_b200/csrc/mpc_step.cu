@@ -102,7 +102,7 @@ extern "C" void ldcbf_params_default(ldcbf_params* p) {
     p->foot_offset = 0.05; p->stop_objective = 0.05;                               // HumanoidMpc.py:200,392
     p->sampling_time = 1e-3;                                                       // HumanoidMpc.py:50
     p->eps_active = 1e-10; p->eps_const_row = 1e-6;
-    p->max_iter = 200; p->reserved = 0;
+    p->max_iter = 200; p->flags = 0;
 }
 
 extern "C" size_t ldcbf_workspace_bytes(int, int, int, int) { return 0; }
@@ -138,7 +138,8 @@ extern "C" int ldcbf_mpc_step_f64(const ldcbf_params* prm, int B, int N, int max
     if (B == 0) return LDCBF_OK;
     if (!x0 || !c_eta) return LDCBF_E_ARG;
     // K1 reads the CoM position straight out of the state rows (p_x, v_x, p_y, v_y): stride 4, y at +2.
-    int rc = launch_halfplanes(B, max_obs, max_verts, x0, 4, 2, verts, nverts, nobs, c_eta, cuda_stream);
+    int rc = launch_halfplanes(B, max_obs, max_verts, x0, 4, 2, verts, nverts, nobs, c_eta,
+                               (prm->flags & LDCBF_FLAG_FAST_GEOMETRY) != 0, cuda_stream);
     if (rc != LDCBF_OK) return rc;
     return ldcbf_mpc_qp_f64(prm, B, N, max_obs, x0, theta0, goal, foot, c_eta, nobs, delta, limits, U, X, theta,
                             omega, obj, status, iters, cuda_stream);

@@ -20,10 +20,10 @@ namespace ldcbf {
 struct RolloutIO {
     double* state; const double* goals; const int8_t* right_first; const double2* verts; const int32_t* nverts;
     const int32_t* nobs; const double* delta; const double* limits; double* traj_X; double* traj_U;
-    int32_t* steps; int32_t* goal_steps; int32_t* status; unsigned long long* total_solves;
+    int32_t* steps; int32_t* goal_steps; int32_t* status; unsigned long long* total_solves; bool fast_geometry;
 };
 
-template <int N, int MO>
+template <int N, int MO, bool EXACT>
 __global__ void __launch_bounds__(128) rollout_kernel(StepConst C, int B, int T, int n_goals, int max_steps_per_goal,
                                                       int substeps, int max_obs, int max_verts, RolloutIO io) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(128) rollout_kernel(StepConst C, int B, int T,
                 ce[o] = make_double4(0.0, 0.0, 0.0, 0.0);
                 if (o < nb) {
                     const int V = min(io.nverts[(size_t)b * max_obs + o], max_verts);
-                    if (V > 0) ce[o] = halfplane_serial(px, py, io.verts + ((size_t)b * max_obs + o) * max_verts, V);
+                    if (V > 0) ce[o] = halfplane_serial<EXACT>(px, py, io.verts + ((size_t)b * max_obs + o) * max_verts, V);
                 }
             }
             int ft[N + 1];
@@ -119,8 +119,11 @@ template <int N, int MO>
 static int launch_rollout(const StepConst& C, int B, int T, int n_goals, int msg, int sub, int max_obs, int max_verts,
                           const RolloutIO& io, cudaStream_t st) {
     const int threads = (B >= 148 * 4 * 128) ? 128 : 32;
-    rollout_kernel<N, MO><<<(unsigned)((B + threads - 1) / threads), threads, 0, st>>>(C, B, T, n_goals, msg, sub,
-                                                                                      max_obs, max_verts, io);
+    const unsigned grid = (unsigned)((B + threads - 1) / threads);
+    if (io.fast_geometry)
+        rollout_kernel<N, MO, false><<<grid, threads, 0, st>>>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io);
+    else
+        rollout_kernel<N, MO, true><<<grid, threads, 0, st>>>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io);
     return check_launch();
 }
 
@@ -152,7 +155,8 @@ extern "C" int ldcbf_rollout_f64(const ldcbf_params* prm, int B, int N, int T, i
     if (sub <= 0) sub = 1;
     const RolloutIO io{state, goals, right_first, reinterpret_cast<const double2*>(verts), nverts, nobs, delta, limits,
                        traj_X, traj_U, steps, goal_steps, status,
-                       reinterpret_cast<unsigned long long*>(total_solves)};
+                       reinterpret_cast<unsigned long long*>(total_solves),
+                       (prm->flags & LDCBF_FLAG_FAST_GEOMETRY) != 0};
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     switch (N) {
         case 1: return dispatch_rollout<1>(C, B, T, n_goals, max_steps_per_goal, sub, max_obs, max_verts, io, st);

@@ -63,8 +63,13 @@ typedef struct ldcbf_params {
     double eps_active;      /* a constraint counts as violated below -eps_active (normalised rows) */
     double eps_const_row;   /* tolerance on the constant k = 0 LDCBF rows (1e-6, BASELINE.json) */
     int32_t max_iter;       /* active-set iteration cap per solve */
-    int32_t reserved;
+    int32_t flags;          /* LDCBF_FLAG_* */
 } ldcbf_params;
+
+/* flags.  Default 0: the half-plane builder restates the reference's arithmetic bit for bit.
+ * FAST_GEOMETRY trades that for ~1 ulp agreement (one reciprocal instead of two square roots and a division per
+ * edge); use it only when bit parity of (c, eta) with the reference is not needed. */
+#define LDCBF_FLAG_FAST_GEOMETRY 1
 
 /* Optional per-scenario overrides of the limits `bounds_tuning.py:22-26` mutates:
  * limits[b] = (ALPHA, V_MAX[0], OMEGA_MAX, OMEGA_MIN).  NaN entries fall back to ldcbf_params. */

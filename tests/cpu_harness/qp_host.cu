@@ -1,0 +1,36 @@
+// TEST INFRASTRUCTURE: compiles the solver source of the CUDA kernels (csrc/mpc_qp.cuh) for the HOST so that the
+// CPU test suite can run the exact same algorithm code without a GPU.  Never linked into libldcbf_b200.so.
+#include "mpc_qp.cuh"
+
+namespace ldcbf { void set_last_error(cudaError_t) {} }
+
+extern "C" int qp_host_solve_n3(const ldcbf_params* prm, int B, int max_obs, const double* x0, const double* theta0,
+                                const double* goal, const int8_t* foot, const double* c_eta, const int32_t* nobs,
+                                const double* delta, double* U, double* X, double* theta, double* omega, double* obj,
+                                int32_t* status, int32_t* iters) {
+    using namespace ldcbf;
+    constexpr int N = 3, MO = 4;
+    const StepConst C = make_const(*prm);
+    for (int b = 0; b < B; ++b) {
+        int ft[N + 1];
+        for (int k = 0; k <= N; ++k) ft[k] = foot[b * (N + 1) + k];
+        double4 ce[MO];
+        const int nb = nobs[b] < MO ? nobs[b] : MO;
+        for (int o = 0; o < MO; ++o) {
+            const double* p = c_eta + ((size_t)b * max_obs + o) * 4;
+            ce[o] = (o < nb) ? make_double4(p[0], p[1], p[2], p[3]) : make_double4(0, 0, 0, 0);
+        }
+        QpSolution<N> S;
+        solve_scenario<N, MO>(C, x0[4 * b], x0[4 * b + 1], x0[4 * b + 2], x0[4 * b + 3], theta0[b], goal[2 * b],
+                              goal[2 * b + 1], ft, ce, nb, delta ? delta[b] : 0.0, C.alpha_over_pi, C.v_max0,
+                              C.omega_max, C.omega_min, S);
+        for (int k = 0; k < N; ++k) { U[(b * N + k) * 2] = S.ux[k]; U[(b * N + k) * 2 + 1] = S.uy[k]; omega[b * N + k] = S.om[k]; }
+        for (int k = 0; k <= N; ++k) {
+            double* x = X + ((size_t)b * (N + 1) + k) * 4;
+            x[0] = S.px[k]; x[1] = S.vx[k]; x[2] = S.py[k]; x[3] = S.vy[k];
+            theta[b * (N + 1) + k] = S.th[k];
+        }
+        obj[b] = S.obj; status[b] = S.status; iters[b] = S.iters;
+    }
+    return 0;
+}

@@ -30,7 +30,7 @@ def cu(a, dt=torch.float64):
 
 
 @pytest.mark.parametrize("name", ("circles", "crowded10", "main_paper"))
-def test_halfplanes_bit_equal_to_oracle(L, name):
+def test_halfplanes_match_oracle_and_reference(L, name):
     from ldcbf_b200 import scenarios
     geo = helpers.load_geo()
     rings = helpers.map_rings(geo, name)
@@ -39,11 +39,27 @@ def test_halfplanes_bit_equal_to_oracle(L, name):
     ce = L.half_planes(cu(Q), cu(verts), cu(nverts, torch.int32), cu(nobs, torch.int32)).cpu().numpy()
     for qi, x in enumerate(Q):
         c, eta = halfplane.half_planes(x, rings)
-        assert np.array_equal(ce[qi, :, :2], c), (name, qi)
+        assert np.array_equal(ce[qi, :, :2], c), (name, qi)          # default mode: bit-equal to the oracle
         assert np.array_equal(ce[qi, :, 2:], eta), (name, qi)
-    # and within 1e-12 of the reference's own output (edge order differs: ConvexHull.simplices vs ring)
+    # and within 1e-12 of the reference's own output (its edge order is ConvexHull.simplices, ours the vertex ring)
     np.testing.assert_allclose(ce[:, :, :2], geo[f"{name}/c"], rtol=0, atol=1e-12)
     np.testing.assert_allclose(ce[:, :, 2:], geo[f"{name}/eta"], rtol=0, atol=1e-12)
+
+
+def test_fast_geometry_flag_within_1e12(L):
+    """LDCBF_FLAG_FAST_GEOMETRY: same half-planes to 1e-12 through the full step entry point."""
+    from ldcbf_b200 import scenarios
+    from ldcbf_b200.binding import FLAG_FAST_GEOMETRY
+    sc = scenarios.config2(512, seed=9)
+    foots = scenarios.foot_window(sc["right_first"], 0, 3)
+    args = (cu(sc["state"][:, :4]), cu(sc["state"][:, 4]), cu(sc["goal"]), cu(foots, torch.int8), cu(sc["verts"]),
+            cu(sc["nverts"], torch.int32), cu(sc["nobs"], torch.int32))
+    a = {k: v.cpu().numpy() for k, v in L.mpc_step(L.default_params(0.4), *args).items()}
+    b = {k: v.cpu().numpy() for k, v in L.mpc_step(L.default_params(0.4, flags=FLAG_FAST_GEOMETRY), *args).items()}
+    np.testing.assert_allclose(a["c_eta"], b["c_eta"], rtol=0, atol=1e-12)
+    assert np.array_equal(a["status"], b["status"])
+    ok = a["status"] == 0
+    np.testing.assert_allclose(a["U"][ok], b["U"][ok], rtol=0, atol=1e-8)
 
 
 def _run_steps(L, states, goals, foots, rings_list, deltas, sampling_time=0.4, N=3):
