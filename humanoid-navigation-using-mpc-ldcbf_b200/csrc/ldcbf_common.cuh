@@ -18,6 +18,7 @@ struct StepConst {
     double alpha_over_pi;
     double l_max_x, l_max_y, l_min_x, l_min_y;
     double v_min0, v_min1, v_max0, v_max1;
+    double legx_mid, legx_half, legy_mid, legy_half, vlat_mid, vlat_half;   // two-sided rows as mid +- half
     double omega_max, omega_min;
     double foot_offset, stop_objective, sampling_time;
     double eps_active, eps_const_row;
@@ -36,6 +37,9 @@ inline StepConst make_const(const ldcbf_params& p) {
     c.alpha_over_pi = p.alpha / 3.141592653589793;
     c.l_max_x = p.l_max_x; c.l_max_y = p.l_max_y; c.l_min_x = p.l_min_x; c.l_min_y = p.l_min_y;
     c.v_min0 = p.v_min[0]; c.v_min1 = p.v_min[1]; c.v_max0 = p.v_max[0]; c.v_max1 = p.v_max[1];
+    c.legx_mid = 0.5 * (p.l_max_x + p.l_min_x); c.legx_half = 0.5 * (p.l_max_x - p.l_min_x);
+    c.legy_mid = 0.5 * (p.l_max_y + p.l_min_y); c.legy_half = 0.5 * (p.l_max_y - p.l_min_y);
+    c.vlat_mid = 0.5 * (p.v_max[1] + p.v_min[1]); c.vlat_half = 0.5 * (p.v_max[1] - p.v_min[1]);
     c.omega_max = p.omega_max; c.omega_min = p.omega_min;
     c.foot_offset = p.foot_offset; c.stop_objective = p.stop_objective; c.sampling_time = p.sampling_time;
     c.eps_active = p.eps_active; c.eps_const_row = p.eps_const_row;

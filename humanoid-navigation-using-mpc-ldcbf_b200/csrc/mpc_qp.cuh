@@ -61,6 +61,13 @@ LDCBF_HD int first_free_slot(unsigned amask) {
     return __builtin_ffs((int)~amask) - 1;
 #endif
 }
+LDCBF_HD unsigned nonneg_bit(double m) {      // 1 when the sign bit of m is clear
+#ifdef __CUDA_ARCH__
+    return ((unsigned)__double2hiint(m) >> 31) ^ 1u;
+#else
+    return m < 0.0 ? 0u : 1u;
+#endif
+}
 LDCBF_HD double quiet_nan() {
 #ifdef __CUDA_ARCH__
     return __longlong_as_double(0x7ff8000000000000LL);
@@ -158,10 +165,15 @@ LDCBF_HD void solve_scenario(const StepConst& C, double p0x, double v0x, double 
             else if (ex[o] * p0x + ey[o] * p0y - hb[o] < -C.eps_const_row) status = LDCBF_STATUS_INFEASIBLE;
         }
     }
-    double vhi[N + 1];
-    vhi[0] = 0.0;
+    // merged longitudinal velocity row at state k: [V_MIN0, min(V_MAX0, V_MAX0 - alpha/pi |omega_{k-1}|)]
+    double vmid[N + 1], vhalf[N + 1];
+    vmid[0] = 0.0; vhalf[0] = 0.0;
 #pragma unroll
-    for (int k = 1; k <= N; ++k) vhi[k] = fmin(vmax0, vmax0 - alpha_over_pi * fabs(S.om[k - 1]));
+    for (int k = 1; k <= N; ++k) {
+        const double vhi = fmin(vmax0, vmax0 - alpha_over_pi * fabs(S.om[k - 1]));
+        vmid[k] = 0.5 * (vhi + C.v_min0);
+        vhalf[k] = 0.5 * (vhi - C.v_min0);
+    }
 
     // ---- Goldfarb-Idnani dual active set on  min 1/2 ||w - g||^2  s.t. rows
     //
@@ -195,38 +207,54 @@ LDCBF_HD void solve_scenario(const StepConst& C, double p0x, double v0x, double 
 
     while (status == LDCBF_STATUS_SOLVED) {
         if (need_scan) {
-            // -- most violated row at the current point (natural units: m, m/s)
-            double best = -C.eps_active, bsg = 0.0;
-            int bid = -1;
-            double Vx = v0x, Vy = v0y;
+            // -- most violated row at the current point (natural units: m, m/s).
+            // A two-sided row lo <= v <= hi has slack  half - |v - mid|  (one value for both sides; the side is
+            // the sign of v - mid, collected as a bit).  All NR slacks are kept in registers, reduced with a
+            // DMNMX tree, and the winner is identified by equality: ~4 instructions per row instead of ~8
+            // compare/select pairs per side.
+            constexpr int NR = 4 * N + N * MO;
+            double sl[NR];
+            unsigned upper = 0;                 // bit i: row i is on the v > mid side
+            {
+                double Vx = v0x, Vy = v0y;
 #pragma unroll
-            for (int k = 0; k < N; ++k) {
-                const double dx = px[k + 1] - px[k], dy = py[k + 1] - py[k];
-                const double lg = rc[k] * dx + rs[k] * dy;
-                const double lt = rc[k] * dy - rs[k] * dx;
-                const double off = (double)ft[k] * C.foot_offset;
-                double s;
-                s = lg - C.l_min_x;          if (s < best) { best = s; bid = 2 * k; bsg = 1.0; }
-                s = C.l_max_x - lg;          if (s < best) { best = s; bid = 2 * k; bsg = -1.0; }
-                s = lt - (C.l_min_y - off);  if (s < best) { best = s; bid = 2 * k + 1; bsg = 1.0; }
-                s = (C.l_max_y - off) - lt;  if (s < best) { best = s; bid = 2 * k + 1; bsg = -1.0; }
-                Vx = C.gtil * dx - Vx; Vy = C.gtil * dy - Vy;       // v_{k+1}
-                const int kk = k + 1;
-                const double vl = rc[kk] * Vx + rs[kk] * Vy;
-                const double vt = (double)ft[kk] * rc[kk] * Vy - rs[kk] * Vx;
-                s = vl - C.v_min0;           if (s < best) { best = s; bid = 2 * N + 2 * k; bsg = 1.0; }
-                s = vhi[kk] - vl;            if (s < best) { best = s; bid = 2 * N + 2 * k; bsg = -1.0; }
-                s = vt - C.v_min1;           if (s < best) { best = s; bid = 2 * N + 2 * k + 1; bsg = 1.0; }
-                s = C.v_max1 - vt;           if (s < best) { best = s; bid = 2 * N + 2 * k + 1; bsg = -1.0; }
+                for (int k = 0; k < N; ++k) {
+                    const double dx = px[k + 1] - px[k], dy = py[k + 1] - py[k];
+                    const double off = (double)ft[k] * C.foot_offset;
+                    double m;
+                    m = (rc[k] * dx + rs[k] * dy) - C.legx_mid;
+                    sl[2 * k] = C.legx_half - fabs(m);
+                    upper |= nonneg_bit(m) << (2 * k);
+                    m = (rc[k] * dy - rs[k] * dx) - (C.legy_mid - off);
+                    sl[2 * k + 1] = C.legy_half - fabs(m);
+                    upper |= nonneg_bit(m) << (2 * k + 1);
+                    Vx = C.gtil * dx - Vx; Vy = C.gtil * dy - Vy;       // v_{k+1}
+                    const int kk = k + 1;
+                    m = (rc[kk] * Vx + rs[kk] * Vy) - vmid[kk];
+                    sl[2 * N + 2 * k] = vhalf[kk] - fabs(m);
+                    upper |= nonneg_bit(m) << (2 * N + 2 * k);
+                    m = ((double)ft[kk] * rc[kk] * Vy - rs[kk] * Vx) - C.vlat_mid;
+                    sl[2 * N + 2 * k + 1] = C.vlat_half - fabs(m);
+                    upper |= nonneg_bit(m) << (2 * N + 2 * k + 1);
 #pragma unroll
-                for (int o = 0; o < MO; ++o) {
-                    if (o < nb) {
-                        s = ex[o] * px[kk] + ey[o] * py[kk] - hb[o];
-                        if (s < best) { best = s; bid = 4 * N + k * MO + o; bsg = 1.0; }
-                    }
+                    for (int o = 0; o < MO; ++o)
+                        sl[4 * N + k * MO + o] = (o < nb) ? ex[o] * px[kk] + ey[o] * py[kk] - hb[o] : INFINITY;
                 }
             }
-            if (bid < 0) break;   // primal feasible: optimal
+            double tr[NR];
+#pragma unroll
+            for (int i = 0; i < NR; ++i) tr[i] = sl[i];
+#pragma unroll
+            for (int n = NR; n > 1; n = (n + 1) / 2) {
+#pragma unroll
+                for (int i = 0; i < n / 2; ++i) tr[i] = fmin(tr[i], tr[n - 1 - i]);
+            }
+            const double best = tr[0];
+            if (!(best < -C.eps_active)) break;   // primal feasible: optimal
+            int bid = 0;
+#pragma unroll
+            for (int i = 1; i < NR; ++i) if (sl[i] == best) bid = i;
+            const double bsg = (bid < 4 * N && ((upper >> bid) & 1u)) ? -1.0 : 1.0;
             row_normal<N, MO>(bid, bsg, C.gtil, rc, rs, ft, ex, ey, np);
             nn = 0.0;
 #pragma unroll

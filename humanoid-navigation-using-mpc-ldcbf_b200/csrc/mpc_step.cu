@@ -45,8 +45,11 @@ __device__ __forceinline__ void load_limits(const StepConst& C, const double* li
     }
 }
 
+#ifndef LDCBF_QP_MINBLOCKS
+#define LDCBF_QP_MINBLOCKS 1
+#endif
 template <int N, int MO>
-__global__ void __launch_bounds__(128) mpc_qp_kernel(StepConst C, int B, int max_obs, StepIO io) {
+__global__ void __launch_bounds__(128, LDCBF_QP_MINBLOCKS) mpc_qp_kernel(StepConst C, int B, int max_obs, StepIO io) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const double4 x = reinterpret_cast<const double4*>(io.x0)[b];          // (p_x, v_x, p_y, v_y)

@@ -7,7 +7,7 @@ from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_size_t, c_void
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libldcbf_b200.so")
+LIB_PATH = os.environ.get("LDCBF_B200_LIB") or os.path.join(_HERE, "libldcbf_b200.so")   # env override: A/B builds
 
 MAX_OBSTACLES = 8      # LDCBF_MAX_OBSTACLES of include/ldcbf_mpc.h
 
