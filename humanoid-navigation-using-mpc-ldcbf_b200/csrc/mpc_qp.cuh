@@ -128,12 +128,22 @@ LDCBF_HD void row_normal(int id, double sg, double gtil, const double (&rc)[N + 
     }
 }
 
+// Per-thread workspace of the solver: the signed normals of the 2N slots and their Gram matrix, 2*(2N)^2 doubles.
+// On the device it lives in shared memory, element e of this thread at ws[e * WS] with WS = threads per block
+// (consecutive threads -> consecutive 8-byte words: conflict-free); a slot is then written with a dynamic
+// address instead of a chain of predicated register moves, and ~110 registers are freed for occupancy.
+template <int N>
+struct QpWorkspace { static constexpr int DOUBLES = 2 * (2 * N) * (2 * N); };
+
 // One scenario.  ce[o] = (c_x, c_y, eta_x, eta_y) for o < nb.
-template <int N, int MO>
+template <int N, int MO, int WS>
 LDCBF_HD void solve_scenario(const StepConst& C, double p0x, double v0x, double p0y, double v0y,
                                                double th0, double gx, double gy, const int (&ft)[N + 1],
                                                const double4 (&ce)[MO], int nb, double delta, double alpha_over_pi,
-                                               double vmax0, double omega_max, double omega_min, QpSolution<N>& S) {
+                                               double vmax0, double omega_max, double omega_min, double* ws,
+                                               QpSolution<N>& S) {
+#define AN(j, i) ws[((j) * NV + (i)) * WS]
+#define GM(i, j) ws[(NV * NV + (i) * NV + (j)) * WS]
     constexpr int NV = 2 * N;
     double rc[N + 1], rs[N + 1];
     // ---- heading schedule (HumanoidMpc.py:137-160)
@@ -190,14 +200,13 @@ LDCBF_HD void solve_scenario(const StepConst& C, double p0x, double v0x, double 
     for (int k = 1; k <= N; ++k) { px[k] = gx; py[k] = gy; }   // unconstrained optimum
 
     unsigned amask = 0;            // occupied slots
-    double An[NV][NV];             // signed normals per slot
     double u[NV];                  // multipliers per slot
-    double G[NV][NV];              // Gram matrix of the slots, lower triangle (i >= j)
+    // AN(j, .): signed normal of slot j;  GM(i, j): Gram matrix of the slots (both triangles are written)
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         u[j] = 0.0;
 #pragma unroll
-        for (int i = 0; i < NV; ++i) { An[j][i] = 0.0; G[j][i] = (i == j) ? 1.0 : 0.0; }
+        for (int i = 0; i < NV; ++i) { AN(j, i) = 0.0; GM(j, i) = (i == j) ? 1.0 : 0.0; }
     }
     int iters = 0;
     bool need_scan = true;
@@ -270,21 +279,21 @@ LDCBF_HD void solve_scenario(const StepConst& C, double p0x, double v0x, double 
         for (int j = 0; j < NV; ++j) {
             double acc = 0.0;
 #pragma unroll
-            for (int i = 0; i < NV; ++i) acc += An[j][i] * np[i];
+            for (int i = 0; i < NV; ++i) acc += AN(j, i) * np[i];
             d[j] = acc;
         }
         {
             double L[NV][NV];      // Cholesky factor, inverse diagonal kept in L[j][j]
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
-                double dj = G[j][j];
+                double dj = GM(j, j);
 #pragma unroll
                 for (int l = 0; l < j; ++l) dj -= L[j][l] * L[j][l];
                 const double inv = rsqrt_f64(fmax(dj, 1e-300));
                 L[j][j] = inv;
 #pragma unroll
                 for (int i = j + 1; i < NV; ++i) {
-                    double v = G[i][j];
+                    double v = GM(i, j);
 #pragma unroll
                     for (int l = 0; l < j; ++l) v -= L[i][l] * L[j][l];
                     L[i][j] = v * inv;
@@ -309,7 +318,7 @@ LDCBF_HD void solve_scenario(const StepConst& C, double p0x, double v0x, double 
         for (int i = 0; i < NV; ++i) {
             double v = np[i];
 #pragma unroll
-            for (int j = 0; j < NV; ++j) v -= r[j] * An[j][i];
+            for (int j = 0; j < NV; ++j) v -= r[j] * AN(j, i);
             z[i] = v;
             zz += v * v;
         }
@@ -340,21 +349,24 @@ LDCBF_HD void solve_scenario(const StepConst& C, double p0x, double v0x, double 
         if (full) { amask |= 1u << slot; need_scan = true; }
         else amask &= ~(1u << slot);
 #pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            if (j == slot) {
-                u[j] = full ? u_p : 0.0;
+        for (int j = 0; j < NV; ++j) if (j == slot) u[j] = full ? u_p : 0.0;
+        {
+            double* an = &AN(slot, 0);             // dynamic slot address
+            double* grow = &GM(slot, 0);
+            double* gcol = &GM(0, slot);
 #pragma unroll
-                for (int i = 0; i < NV; ++i) An[j][i] = full ? np[i] : 0.0;
+            for (int i = 0; i < NV; ++i) an[i * WS] = full ? np[i] : 0.0;
 #pragma unroll
-                for (int l = 0; l < NV; ++l) {
-                    const double val = full ? d[l] : 0.0;
-                    if (l < j) G[j][l] = val;
-                    else if (l > j) G[l][j] = val;
-                }
-                G[j][j] = full ? nn : 1.0;
+            for (int l = 0; l < NV; ++l) {
+                const double val = full ? d[l] : 0.0;   // d[slot] = 0 for a free slot; the diagonal is set below
+                grow[l * WS] = val;
+                gcol[l * NV * WS] = val;
             }
+            grow[slot * WS] = full ? nn : 1.0;
         }
     }
+#undef AN
+#undef GM
 
     // ---- outputs: states, footsteps, objective
     S.status = status;

@@ -45,12 +45,12 @@ __device__ __forceinline__ void load_limits(const StepConst& C, const double* li
     }
 }
 
-#ifndef LDCBF_QP_MINBLOCKS
-#define LDCBF_QP_MINBLOCKS 1
-#endif
-template <int N, int MO>
-__global__ void __launch_bounds__(128, LDCBF_QP_MINBLOCKS) mpc_qp_kernel(StepConst C, int B, int max_obs, StepIO io) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+// One thread per scenario; BLOCK threads per block (32 for small batches so the warps spread over all SMs, 128
+// otherwise).  Dynamic shared memory: QpWorkspace<N>::DOUBLES doubles per thread, element-major.
+template <int N, int MO, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) mpc_qp_kernel(StepConst C, int B, int max_obs, StepIO io) {
+    extern __shared__ double qp_ws[];
+    const int b = blockIdx.x * BLOCK + threadIdx.x;
     if (b >= B) return;
     const double4 x = reinterpret_cast<const double4*>(io.x0)[b];          // (p_x, v_x, p_y, v_y)
     const double2 g = reinterpret_cast<const double2*>(io.goal)[b];
@@ -65,19 +65,28 @@ __global__ void __launch_bounds__(128, LDCBF_QP_MINBLOCKS) mpc_qp_kernel(StepCon
 #pragma unroll
     for (int o = 0; o < MO; ++o) ce[o] = (o < nb) ? gce[o] : make_double4(0.0, 0.0, 0.0, 0.0);
     QpSolution<N> S;
-    solve_scenario<N, MO>(C, x.x, x.y, x.z, x.w, io.theta0[b], g.x, g.y, ft, ce, nb,
-                          io.delta ? io.delta[b] : 0.0, aop, vmax0, omax, omin, S);
+    solve_scenario<N, MO, BLOCK>(C, x.x, x.y, x.z, x.w, io.theta0[b], g.x, g.y, ft, ce, nb,
+                                 io.delta ? io.delta[b] : 0.0, aop, vmax0, omax, omin, qp_ws + threadIdx.x, S);
     store_solution<N>(S, b, io.U, io.X, io.theta, io.omega, io.obj, io.status, io.iters);
+}
+
+template <int N, int MO, int BLOCK>
+static int launch_qp_block(const StepConst& C, int B, int max_obs, const StepIO& io, cudaStream_t st) {
+    const size_t smem = (size_t)QpWorkspace<N>::DOUBLES * sizeof(double) * BLOCK;
+    auto kern = mpc_qp_kernel<N, MO, BLOCK>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_last_error(e); return LDCBF_E_LAUNCH; }
+    }
+    kern<<<(unsigned)((B + BLOCK - 1) / BLOCK), BLOCK, smem, st>>>(C, B, max_obs, io);
+    return check_launch();
 }
 
 template <int N, int MO>
 static int launch_qp(const StepConst& C, int B, int max_obs, const StepIO& io, cudaStream_t st) {
-    // small batches: one warp per block so that the warps spread over all SMs (latency-bound regime);
-    // large batches: 128-thread blocks.
-    const int threads = (B >= 148 * 4 * 128) ? 128 : 32;
-    const unsigned grid = (unsigned)((B + threads - 1) / threads);
-    mpc_qp_kernel<N, MO><<<grid, threads, 0, st>>>(C, B, max_obs, io);
-    return check_launch();
+    // small batches: one warp per block so that the warps spread over all SMs (latency-bound regime)
+    if (B >= 148 * 4 * 128) return launch_qp_block<N, MO, 128>(C, B, max_obs, io, st);
+    return launch_qp_block<N, MO, 32>(C, B, max_obs, io, st);
 }
 
 template <int N>

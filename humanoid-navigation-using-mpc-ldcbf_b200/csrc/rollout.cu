@@ -23,10 +23,11 @@ struct RolloutIO {
     int32_t* steps; int32_t* goal_steps; int32_t* status; unsigned long long* total_solves; bool fast_geometry;
 };
 
-template <int N, int MO, bool EXACT>
-__global__ void __launch_bounds__(128) rollout_kernel(StepConst C, int B, int T, int n_goals, int max_steps_per_goal,
+template <int N, int MO, bool EXACT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int T, int n_goals, int max_steps_per_goal,
                                                       int substeps, int max_obs, int max_verts, RolloutIO io) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ double qp_ws[];
+    const int b = blockIdx.x * BLOCK + threadIdx.x;
     if (b >= B) return;
     double px = io.state[5 * (size_t)b], vx = io.state[5 * (size_t)b + 1], py = io.state[5 * (size_t)b + 2],
            vy = io.state[5 * (size_t)b + 3], th = io.state[5 * (size_t)b + 4];
@@ -74,7 +75,8 @@ __global__ void __launch_bounds__(128) rollout_kernel(StepConst C, int B, int T,
 #pragma unroll
             for (int k = 0; k <= N; ++k) ft[k] = (((step_number + k) & 1) == (right_first ? 0 : 1)) ? 1 : -1;
             QpSolution<N> S;
-            solve_scenario<N, MO>(C, px, vx, py, vy, th, gx, gy, ft, ce, nb, dl, aop, vmax0, omax, omin, S);
+            solve_scenario<N, MO, BLOCK>(C, px, vx, py, vy, th, gx, gy, ft, ce, nb, dl, aop, vmax0, omax, omin,
+                                         qp_ws + threadIdx.x, S);
             ++solves;
             last_status = S.status;
             if (S.status != LDCBF_STATUS_SOLVED) {                                    // :419-429 break
@@ -115,16 +117,28 @@ __global__ void __launch_bounds__(128) rollout_kernel(StepConst C, int B, int T,
     }
 }
 
+template <int N, int MO, bool EXACT, int BLOCK>
+static int launch_rollout_block(const StepConst& C, int B, int T, int n_goals, int msg, int sub, int max_obs,
+                                int max_verts, const RolloutIO& io, cudaStream_t st) {
+    const size_t smem = (size_t)QpWorkspace<N>::DOUBLES * sizeof(double) * BLOCK;
+    auto kern = rollout_kernel<N, MO, EXACT, BLOCK>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_last_error(e); return LDCBF_E_LAUNCH; }
+    }
+    kern<<<(unsigned)((B + BLOCK - 1) / BLOCK), BLOCK, smem, st>>>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io);
+    return check_launch();
+}
+
 template <int N, int MO>
 static int launch_rollout(const StepConst& C, int B, int T, int n_goals, int msg, int sub, int max_obs, int max_verts,
                           const RolloutIO& io, cudaStream_t st) {
-    const int threads = (B >= 148 * 4 * 128) ? 128 : 32;
-    const unsigned grid = (unsigned)((B + threads - 1) / threads);
+    const bool big = B >= 148 * 4 * 128;
     if (io.fast_geometry)
-        rollout_kernel<N, MO, false><<<grid, threads, 0, st>>>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io);
-    else
-        rollout_kernel<N, MO, true><<<grid, threads, 0, st>>>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io);
-    return check_launch();
+        return big ? launch_rollout_block<N, MO, false, 128>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st)
+                   : launch_rollout_block<N, MO, false, 32>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
+    return big ? launch_rollout_block<N, MO, true, 128>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st)
+               : launch_rollout_block<N, MO, true, 32>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
 }
 
 template <int N>

@@ -21,9 +21,10 @@ extern "C" int qp_host_solve_n3(const ldcbf_params* prm, int B, int max_obs, con
             ce[o] = (o < nb) ? make_double4(p[0], p[1], p[2], p[3]) : make_double4(0, 0, 0, 0);
         }
         QpSolution<N> S;
-        solve_scenario<N, MO>(C, x0[4 * b], x0[4 * b + 1], x0[4 * b + 2], x0[4 * b + 3], theta0[b], goal[2 * b],
+        double ws[QpWorkspace<N>::DOUBLES];
+        solve_scenario<N, MO, 1>(C, x0[4 * b], x0[4 * b + 1], x0[4 * b + 2], x0[4 * b + 3], theta0[b], goal[2 * b],
                               goal[2 * b + 1], ft, ce, nb, delta ? delta[b] : 0.0, C.alpha_over_pi, C.v_max0,
-                              C.omega_max, C.omega_min, S);
+                              C.omega_max, C.omega_min, ws, S);
         for (int k = 0; k < N; ++k) { U[(b * N + k) * 2] = S.ux[k]; U[(b * N + k) * 2 + 1] = S.uy[k]; omega[b * N + k] = S.om[k]; }
         for (int k = 0; k <= N; ++k) {
             double* x = X + ((size_t)b * (N + 1) + k) * 4;
