@@ -12,6 +12,8 @@
 // stride (in 16-byte units) so the 32 lanes of a warp hit 32 different bank groups.
 // 16*E bytes in and 32 bytes out per obstacle against ~95 (bit-exact arithmetic) / ~50 (fast arithmetic)
 // instructions per edge: see DESIGN.md §6 for where that puts the kernel between the HBM and FP64 rooflines.
+#include <cuda_pipeline.h>
+
 #include "halfplane_dev.cuh"
 
 namespace ldcbf {
@@ -40,10 +42,13 @@ __global__ void __launch_bounds__(K1_THREADS) halfplane_kernel(int n_pairs, int 
     // coalesced staging of the block's contiguous vertex range
     const double2* g = verts + (size_t)pair0 * max_verts;
     const int total = K1_THREADS * max_verts;
+    // cp.async (LDGSTS): all of a thread's 16-byte copies are in flight at once, no register staging
     for (int i = threadIdx.x; i < total; i += K1_THREADS) {
         const int lp = i / max_verts, e = i - lp * max_verts;
-        if (e < sV[lp]) srings[lp * sstride + e] = __ldg(g + i);
+        if (e < sV[lp]) __pipeline_memcpy_async(srings + lp * sstride + e, g + i, sizeof(double2));
     }
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
     __syncthreads();
     if (pair >= n_pairs) return;
     if (V <= 0) { c_eta[pair] = make_double4(0.0, 0.0, 0.0, 0.0); return; }

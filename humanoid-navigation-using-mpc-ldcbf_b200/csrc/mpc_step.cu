@@ -84,14 +84,16 @@ static int launch_qp_block(const StepConst& C, int B, int max_obs, const StepIO&
 
 template <int N, int MO>
 static int launch_qp(const StepConst& C, int B, int max_obs, const StepIO& io, cudaStream_t st) {
-    // small batches: one warp per block so that the warps spread over all SMs (latency-bound regime)
+    // Large batches: 128-thread blocks.  Small batches leave SM sub-partitions idle, so the scenarios are spread
+    // over more, narrower warps (8 lanes used per warp): a warp runs until its slowest lane has converged, and the
+    // expected maximum iteration count over 8 scenarios is well below that over 32.
     if (B >= 148 * 4 * 128) return launch_qp_block<N, MO, 128>(C, B, max_obs, io, st);
-    return launch_qp_block<N, MO, 32>(C, B, max_obs, io, st);
+    if (B >= 148 * 4 * 16) return launch_qp_block<N, MO, 32>(C, B, max_obs, io, st);
+    return launch_qp_block<N, MO, 8>(C, B, max_obs, io, st);
 }
 
 template <int N>
 static int dispatch_obs(const StepConst& C, int B, int max_obs, const StepIO& io, cudaStream_t st) {
-    if (max_obs <= 2) return launch_qp<N, 2>(C, B, max_obs, io, st);
     if (max_obs <= 4) return launch_qp<N, 4>(C, B, max_obs, io, st);
     if (max_obs <= LDCBF_MAX_OBSTACLES) return launch_qp<N, 8>(C, B, max_obs, io, st);
     return LDCBF_E_SHAPE;

@@ -144,7 +144,6 @@ static int launch_rollout(const StepConst& C, int B, int T, int n_goals, int msg
 template <int N>
 static int dispatch_rollout(const StepConst& C, int B, int T, int n_goals, int msg, int sub, int max_obs,
                             int max_verts, const RolloutIO& io, cudaStream_t st) {
-    if (max_obs <= 2) return launch_rollout<N, 2>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
     if (max_obs <= 4) return launch_rollout<N, 4>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
     if (max_obs <= LDCBF_MAX_OBSTACLES) return launch_rollout<N, 8>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
     return LDCBF_E_SHAPE;
