@@ -47,9 +47,16 @@ LDCBF_HD double mul_rn(double a, double b) {
     volatile double r = a * b; return r;
 #endif
 }
+// 1/sqrt(x) for the Cholesky pivots (x > 0, normal range): hardware seed (MUFU.RSQ64H, ~20 bits) and two
+// Newton steps, ~10 instructions instead of the ~20 of the library rsqrt with its special-case handling.
 LDCBF_HD double rsqrt_f64(double x) {
 #ifdef __CUDA_ARCH__
-    return rsqrt(x);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    y = y * (1.5 - hx * y * y);
+    y = y * (1.5 - hx * y * y);
+    return y;
 #else
     return 1.0 / sqrt(x);
 #endif
@@ -131,259 +138,286 @@ LDCBF_HD void row_normal(int id, double sg, double gtil, const double (&rc)[N + 
 // Per-thread workspace of the solver: the signed normals of the 2N slots and their Gram matrix, 2*(2N)^2 doubles.
 // On the device it lives in shared memory, element e of this thread at ws[e * WS] with WS = threads per block
 // (consecutive threads -> consecutive 8-byte words: conflict-free); a slot is then written with a dynamic
-// address instead of a chain of predicated register moves, and ~110 registers are freed for occupancy.
+// address instead of a chain of predicated register moves, and ~110 registers are freed.
 template <int N>
 struct QpWorkspace { static constexpr int DOUBLES = 2 * (2 * N) * (2 * N); };
 
-// One scenario.  ce[o] = (c_x, c_y, eta_x, eta_y) for o < nb.
-template <int N, int MO, int WS>
-LDCBF_HD void solve_scenario(const StepConst& C, double p0x, double v0x, double p0y, double v0y,
-                                               double th0, double gx, double gy, const int (&ft)[N + 1],
-                                               const double4 (&ce)[MO], int nb, double delta, double alpha_over_pi,
-                                               double vmax0, double omega_max, double omega_min, double* ws,
-                                               QpSolution<N>& S) {
+// Solver state of one scenario, kept in registers across trips of the active-set loop.
+template <int N, int MO>
+struct QpState {
+    double rc[N + 1], rs[N + 1];          // cos / sin of the heading schedule
+    double th[N + 1], om[N];
+    int ft[N + 1];                        // foot parity window
+    double ex[MO], ey[MO], hb[MO];        // half-planes: eta . p >= hb
+    int nb;
+    double vmid[N + 1], vhalf[N + 1];     // merged longitudinal velocity row at state k: mid +- half
+    double p0x, p0y, v0x, v0y, gx, gy;
+    double px[N + 1], py[N + 1];          // current iterate w = (p_1..p_N), p_0 fixed
+    double u[2 * N];                      // multipliers per slot
+    double np[2 * N], nn, s_p, u_p;       // row being added: signed normal, |n|^2, slack, multiplier
+    unsigned amask;                       // occupied slots
+    int status, iters;
+    bool need_scan, done;
+};
+
 #define AN(j, i) ws[((j) * NV + (i)) * WS]
 #define GM(i, j) ws[(NV * NV + (i) * NV + (j)) * WS]
+
+// Heading schedule, half-plane offsets, row bounds, unconstrained optimum, empty active set.
+// ce[o] = (c_x, c_y, eta_x, eta_y) for o < nb.
+template <int N, int MO, int WS>
+LDCBF_HD void qp_setup(const StepConst& C, double p0x, double v0x, double p0y, double v0y, double th0, double gx,
+                       double gy, const int (&ft)[N + 1], const double4 (&ce)[MO], int nb, double delta,
+                       double alpha_over_pi, double vmax0, double omega_max, double omega_min, double* ws,
+                       QpState<N, MO>& s) {
     constexpr int NV = 2 * N;
-    double rc[N + 1], rs[N + 1];
+    s.p0x = p0x; s.p0y = p0y; s.v0x = v0x; s.v0y = v0y; s.gx = gx; s.gy = gy; s.nb = nb;
+#pragma unroll
+    for (int k = 0; k <= N; ++k) s.ft[k] = ft[k];
     // ---- heading schedule (HumanoidMpc.py:137-160)
     {
         const double phi = atan2(gy - p0y, gx - p0x);
         double thk = th0;
-        S.th[0] = thk;
-        sincos(thk, &rs[0], &rc[0]);
+        s.th[0] = thk;
+        sincos(thk, &s.rs[0], &s.rc[0]);
 #pragma unroll
         for (int k = 0; k < N; ++k) {
             const double w = fmin(fmax(phi - thk, omega_min), omega_max);
-            S.om[k] = w;
+            s.om[k] = w;
             thk = add_rn(thk, mul_rn(w, C.sampling_time));
-            S.th[k + 1] = thk;
-            sincos(thk, &rs[k + 1], &rc[k + 1]);
+            s.th[k + 1] = thk;
+            sincos(thk, &s.rs[k + 1], &s.rc[k + 1]);
         }
     }
     // ---- half-planes: eta_o . p >= eta_o . c_o + delta
-    double ex[MO], ey[MO], hb[MO];
     int status = LDCBF_STATUS_SOLVED;
 #pragma unroll
     for (int o = 0; o < MO; ++o) {
-        ex[o] = 0.0; ey[o] = 0.0; hb[o] = -1.0;
+        s.ex[o] = 0.0; s.ey[o] = 0.0; s.hb[o] = -1.0;
         if (o < nb) {
-            ex[o] = ce[o].z; ey[o] = ce[o].w;
-            hb[o] = ce[o].z * ce[o].x + ce[o].w * ce[o].y + delta;
-            if (!(ex[o] == ex[o]) || !(ey[o] == ey[o])) status = LDCBF_STATUS_DEGENERATE;
+            s.ex[o] = ce[o].z; s.ey[o] = ce[o].w;
+            s.hb[o] = ce[o].z * ce[o].x + ce[o].w * ce[o].y + delta;
+            if (!(s.ex[o] == s.ex[o]) || !(s.ey[o] == s.ey[o])) status = LDCBF_STATUS_DEGENERATE;
             // constant k = 0 row (HumanoidMpc.py:284-292 with k = 0)
-            else if (ex[o] * p0x + ey[o] * p0y - hb[o] < -C.eps_const_row) status = LDCBF_STATUS_INFEASIBLE;
+            else if (s.ex[o] * p0x + s.ey[o] * p0y - s.hb[o] < -C.eps_const_row) status = LDCBF_STATUS_INFEASIBLE;
         }
     }
     // merged longitudinal velocity row at state k: [V_MIN0, min(V_MAX0, V_MAX0 - alpha/pi |omega_{k-1}|)]
-    double vmid[N + 1], vhalf[N + 1];
-    vmid[0] = 0.0; vhalf[0] = 0.0;
+    s.vmid[0] = 0.0; s.vhalf[0] = 0.0;
 #pragma unroll
     for (int k = 1; k <= N; ++k) {
-        const double vhi = fmin(vmax0, vmax0 - alpha_over_pi * fabs(S.om[k - 1]));
-        vmid[k] = 0.5 * (vhi + C.v_min0);
-        vhalf[k] = 0.5 * (vhi - C.v_min0);
+        const double vhi = fmin(vmax0, vmax0 - alpha_over_pi * fabs(s.om[k - 1]));
+        s.vmid[k] = 0.5 * (vhi + C.v_min0);
+        s.vhalf[k] = 0.5 * (vhi - C.v_min0);
     }
-
-    // ---- Goldfarb-Idnani dual active set on  min 1/2 ||w - g||^2  s.t. rows
-    //
-    // Active normals live in NV fixed slots (free slot: zero normal).  G is the slots' Gram matrix (identity on
-    // free slots), updated in place when a row enters or leaves; each step factorises it from scratch (a fully
-    // unrolled NV x NV Cholesky): r = G^-1 (N^T n+), z = n+ - N r.  Updating the inverse instead (one rank-1
-    // update per add / drop) was measured 30 % faster but loses the active set on ill-conditioned vertices
-    // (two nearly anti-parallel velocity rows, multipliers ~3e4): a false "infeasible" in 1 of 4096 scenarios.
-    // One loop, one step per trip: every lane of the warp runs the same instruction stream and lanes differ
-    // only in how many trips they need.
-    double px[N + 1], py[N + 1];
-    px[0] = p0x; py[0] = p0y;
+    // ---- Goldfarb-Idnani dual active set on  min 1/2 ||w - g||^2  s.t. rows: start at the unconstrained optimum
+    s.px[0] = p0x; s.py[0] = p0y;
 #pragma unroll
-    for (int k = 1; k <= N; ++k) { px[k] = gx; py[k] = gy; }   // unconstrained optimum
-
-    unsigned amask = 0;            // occupied slots
-    double u[NV];                  // multipliers per slot
-    // AN(j, .): signed normal of slot j;  GM(i, j): Gram matrix of the slots (both triangles are written)
+    for (int k = 1; k <= N; ++k) { s.px[k] = gx; s.py[k] = gy; }
+    s.amask = 0;
+    // AN(j, .): signed normal of slot j (zero when free);  GM(i, j): Gram matrix of the slots (identity on free slots)
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-        u[j] = 0.0;
+        s.u[j] = 0.0; s.np[j] = 0.0;
 #pragma unroll
         for (int i = 0; i < NV; ++i) { AN(j, i) = 0.0; GM(j, i) = (i == j) ? 1.0 : 0.0; }
     }
-    int iters = 0;
-    bool need_scan = true;
-    double np[NV], nn = 1.0, s_p = 0.0, u_p = 0.0;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) np[i] = 0.0;
+    s.nn = 1.0; s.s_p = 0.0; s.u_p = 0.0;
+    s.iters = 0;
+    s.need_scan = true;
+    s.status = status;
+    s.done = status != LDCBF_STATUS_SOLVED;
+}
 
-    while (status == LDCBF_STATUS_SOLVED) {
-        if (need_scan) {
-            // -- most violated row at the current point (natural units: m, m/s).
-            // A two-sided row lo <= v <= hi has slack  half - |v - mid|  (one value for both sides; the side is
-            // the sign of v - mid, collected as a bit).  All NR slacks are kept in registers, reduced with a
-            // DMNMX tree, and the winner is identified by equality: ~4 instructions per row instead of ~8
-            // compare/select pairs per side.
-            constexpr int NR = 4 * N + N * MO;
-            double sl[NR];
-            unsigned upper = 0;                 // bit i: row i is on the v > mid side
-            {
-                double Vx = v0x, Vy = v0y;
+// One trip of the active-set loop: (scan for the most violated row if the previous trip ended with a full step,)
+// one primal/dual step, one slot update.  Every lane of a warp runs the same instruction stream; lanes differ
+// only in how many trips they need.  Sets s.done on convergence or failure.
+//
+// Each trip factorises the slots' Gram matrix from scratch (fully unrolled NV x NV Cholesky): r = G^-1 (N^T n+),
+// z = n+ - N r.  Updating the inverse instead (one rank-1 update per add / drop) was measured 30 % faster but
+// loses the active set on ill-conditioned vertices (two nearly anti-parallel velocity rows, multipliers ~3e4):
+// a false "infeasible" in 1 of 4096 scenarios.
+template <int N, int MO, int WS>
+LDCBF_HD void qp_trip(const StepConst& C, double* ws, QpState<N, MO>& s) {
+    constexpr int NV = 2 * N;
+    if (s.need_scan) {
+        // -- most violated row at the current point (natural units: m, m/s).
+        // A two-sided row lo <= v <= hi has slack  half - |v - mid|  (one value for both sides; the side is the
+        // sign of v - mid, collected as a bit).  The NR slacks are reduced by a tournament over (value, index)
+        // pairs (fmin on doubles costs ~7 instructions on sm_100: NaN handling, no DMNMX).
+        constexpr int NR = 4 * N + N * MO;
+        double sl[NR];
+        unsigned upper = 0;                 // bit i: row i is on the v > mid side
+        {
+            double Vx = s.v0x, Vy = s.v0y;
 #pragma unroll
-                for (int k = 0; k < N; ++k) {
-                    const double dx = px[k + 1] - px[k], dy = py[k + 1] - py[k];
-                    const double off = (double)ft[k] * C.foot_offset;
-                    double m;
-                    m = (rc[k] * dx + rs[k] * dy) - C.legx_mid;
-                    sl[2 * k] = C.legx_half - fabs(m);
-                    upper |= nonneg_bit(m) << (2 * k);
-                    m = (rc[k] * dy - rs[k] * dx) - (C.legy_mid - off);
-                    sl[2 * k + 1] = C.legy_half - fabs(m);
-                    upper |= nonneg_bit(m) << (2 * k + 1);
-                    Vx = C.gtil * dx - Vx; Vy = C.gtil * dy - Vy;       // v_{k+1}
-                    const int kk = k + 1;
-                    m = (rc[kk] * Vx + rs[kk] * Vy) - vmid[kk];
-                    sl[2 * N + 2 * k] = vhalf[kk] - fabs(m);
-                    upper |= nonneg_bit(m) << (2 * N + 2 * k);
-                    m = ((double)ft[kk] * rc[kk] * Vy - rs[kk] * Vx) - C.vlat_mid;
-                    sl[2 * N + 2 * k + 1] = C.vlat_half - fabs(m);
-                    upper |= nonneg_bit(m) << (2 * N + 2 * k + 1);
+            for (int k = 0; k < N; ++k) {
+                const double dx = s.px[k + 1] - s.px[k], dy = s.py[k + 1] - s.py[k];
+                const double off = (double)s.ft[k] * C.foot_offset;
+                double m;
+                m = (s.rc[k] * dx + s.rs[k] * dy) - C.legx_mid;
+                sl[2 * k] = C.legx_half - fabs(m);
+                upper |= nonneg_bit(m) << (2 * k);
+                m = (s.rc[k] * dy - s.rs[k] * dx) - (C.legy_mid - off);
+                sl[2 * k + 1] = C.legy_half - fabs(m);
+                upper |= nonneg_bit(m) << (2 * k + 1);
+                Vx = C.gtil * dx - Vx; Vy = C.gtil * dy - Vy;       // v_{k+1}
+                const int kk = k + 1;
+                m = (s.rc[kk] * Vx + s.rs[kk] * Vy) - s.vmid[kk];
+                sl[2 * N + 2 * k] = s.vhalf[kk] - fabs(m);
+                upper |= nonneg_bit(m) << (2 * N + 2 * k);
+                m = ((double)s.ft[kk] * s.rc[kk] * Vy - s.rs[kk] * Vx) - C.vlat_mid;
+                sl[2 * N + 2 * k + 1] = C.vlat_half - fabs(m);
+                upper |= nonneg_bit(m) << (2 * N + 2 * k + 1);
 #pragma unroll
-                    for (int o = 0; o < MO; ++o)
-                        sl[4 * N + k * MO + o] = (o < nb) ? ex[o] * px[kk] + ey[o] * py[kk] - hb[o] : INFINITY;
-                }
+                for (int o = 0; o < MO; ++o)
+                    sl[4 * N + k * MO + o] = (o < s.nb) ? s.ex[o] * s.px[kk] + s.ey[o] * s.py[kk] - s.hb[o] : INFINITY;
             }
-            double tr[NR];
-#pragma unroll
-            for (int i = 0; i < NR; ++i) tr[i] = sl[i];
-#pragma unroll
-            for (int n = NR; n > 1; n = (n + 1) / 2) {
-#pragma unroll
-                for (int i = 0; i < n / 2; ++i) tr[i] = fmin(tr[i], tr[n - 1 - i]);
-            }
-            const double best = tr[0];
-            if (!(best < -C.eps_active)) break;   // primal feasible: optimal
-            int bid = 0;
-#pragma unroll
-            for (int i = 1; i < NR; ++i) if (sl[i] == best) bid = i;
-            const double bsg = (bid < 4 * N && ((upper >> bid) & 1u)) ? -1.0 : 1.0;
-            row_normal<N, MO>(bid, bsg, C.gtil, rc, rs, ft, ex, ey, np);
-            nn = 0.0;
-#pragma unroll
-            for (int i = 0; i < NV; ++i) nn += np[i] * np[i];
-            s_p = best; u_p = 0.0;
-            need_scan = false;
         }
-        if (++iters > C.max_iter) { status = LDCBF_STATUS_MAX_ITER; break; }
+        // tournament argmin: (value, index) pairs, one compare and three selects per node
+        int ti[NR];
+#pragma unroll
+        for (int i = 0; i < NR; ++i) ti[i] = i;
+#pragma unroll
+        for (int n = NR; n > 1; n = (n + 1) / 2) {
+#pragma unroll
+            for (int i = 0; i < n / 2; ++i) {
+                const bool take = sl[n - 1 - i] < sl[i];
+                sl[i] = take ? sl[n - 1 - i] : sl[i];
+                ti[i] = take ? ti[n - 1 - i] : ti[i];
+            }
+        }
+        const double best = sl[0];
+        if (!(best < -C.eps_active)) { s.done = true; return; }   // primal feasible: optimal
+        const int bid = ti[0];
+        const double bsg = (bid < 4 * N && ((upper >> bid) & 1u)) ? -1.0 : 1.0;
+        row_normal<N, MO>(bid, bsg, C.gtil, s.rc, s.rs, s.ft, s.ex, s.ey, s.np);
+        double nn = 0.0;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) nn += s.np[i] * s.np[i];
+        s.nn = nn; s.s_p = best; s.u_p = 0.0;
+        s.need_scan = false;
+    }
+    if (++s.iters > C.max_iter) { s.status = LDCBF_STATUS_MAX_ITER; s.done = true; return; }
 
-        // d = N^T n+ ;  r = G^-1 d ;  z = n+ - N r
-        double d[NV], r[NV], z[NV], zz = 0.0;
+    // d = N^T n+ ;  r = G^-1 d ;  z = n+ - N r
+    double d[NV], r[NV], z[NV], zz = 0.0;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) acc += AN(j, i) * s.np[i];
+        d[j] = acc;
+    }
+    {
+        double L[NV][NV];      // Cholesky factor, inverse diagonal kept in L[j][j]
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            double acc = 0.0;
+            double dj = GM(j, j);
 #pragma unroll
-            for (int i = 0; i < NV; ++i) acc += AN(j, i) * np[i];
-            d[j] = acc;
-        }
-        {
-            double L[NV][NV];      // Cholesky factor, inverse diagonal kept in L[j][j]
+            for (int l = 0; l < j; ++l) dj -= L[j][l] * L[j][l];
+            const double inv = rsqrt_f64(fmax(dj, 1e-300));
+            L[j][j] = inv;
 #pragma unroll
-            for (int j = 0; j < NV; ++j) {
-                double dj = GM(j, j);
+            for (int i = j + 1; i < NV; ++i) {
+                double v = GM(i, j);
 #pragma unroll
-                for (int l = 0; l < j; ++l) dj -= L[j][l] * L[j][l];
-                const double inv = rsqrt_f64(fmax(dj, 1e-300));
-                L[j][j] = inv;
-#pragma unroll
-                for (int i = j + 1; i < NV; ++i) {
-                    double v = GM(i, j);
-#pragma unroll
-                    for (int l = 0; l < j; ++l) v -= L[i][l] * L[j][l];
-                    L[i][j] = v * inv;
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < NV; ++j) {
-                double v = d[j];
-#pragma unroll
-                for (int l = 0; l < j; ++l) v -= L[j][l] * r[l];
-                r[j] = v * L[j][j];
-            }
-#pragma unroll
-            for (int j = NV - 1; j >= 0; --j) {
-                double v = r[j];
-#pragma unroll
-                for (int l = j + 1; l < NV; ++l) v -= L[l][j] * r[l];
-                r[j] = v * L[j][j];
+                for (int l = 0; l < j; ++l) v -= L[i][l] * L[j][l];
+                L[i][j] = v * inv;
             }
         }
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            double v = np[i];
-#pragma unroll
-            for (int j = 0; j < NV; ++j) v -= r[j] * AN(j, i);
-            z[i] = v;
-            zz += v * v;
-        }
-        const bool dependent = !(zz > 1e-13 * nn) || amask == (1u << NV) - 1u;
-        // dual step length t1 = min u_j / r_j over r_j > 0, compared by cross-multiplication
-        double t1n = 1.0, t1d = 0.0;          // t1 = t1n / t1d, "infinite" while t1d == 0
-        int ldrop = -1;
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            if (((amask >> j) & 1u) && r[j] > 1e-13) {
-                if (ldrop < 0 || u[j] * t1d < t1n * r[j]) { t1n = u[j]; t1d = r[j]; ldrop = j; }
-            }
+            double v = d[j];
+#pragma unroll
+            for (int l = 0; l < j; ++l) v -= L[j][l] * r[l];
+            r[j] = v * L[j][j];
         }
-        // full step t2 = -s_p / zz
-        const bool full = !dependent && (ldrop < 0 || (-s_p) * t1d <= t1n * zz);
-        if (!full && ldrop < 0) { status = LDCBF_STATUS_INFEASIBLE; break; }
-        const double t = full ? (-s_p) / zz : t1n / t1d;
 #pragma unroll
-        for (int j = 0; j < NV; ++j) u[j] -= t * r[j];
-        u_p += t;
-        if (!dependent) {
+        for (int j = NV - 1; j >= 0; --j) {
+            double v = r[j];
 #pragma unroll
-            for (int k = 1; k <= N; ++k) { px[k] += t * z[2 * (k - 1)]; py[k] += t * z[2 * (k - 1) + 1]; }
-            s_p += t * zz;
-        }
-        // -- slot bookkeeping: row p enters the first free slot (full step) or slot ldrop leaves (partial step)
-        const int slot = full ? first_free_slot(amask) : ldrop;
-        if (full) { amask |= 1u << slot; need_scan = true; }
-        else amask &= ~(1u << slot);
-#pragma unroll
-        for (int j = 0; j < NV; ++j) if (j == slot) u[j] = full ? u_p : 0.0;
-        {
-            double* an = &AN(slot, 0);             // dynamic slot address
-            double* grow = &GM(slot, 0);
-            double* gcol = &GM(0, slot);
-#pragma unroll
-            for (int i = 0; i < NV; ++i) an[i * WS] = full ? np[i] : 0.0;
-#pragma unroll
-            for (int l = 0; l < NV; ++l) {
-                const double val = full ? d[l] : 0.0;   // d[slot] = 0 for a free slot; the diagonal is set below
-                grow[l * WS] = val;
-                gcol[l * NV * WS] = val;
-            }
-            grow[slot * WS] = full ? nn : 1.0;
+            for (int l = j + 1; l < NV; ++l) v -= L[l][j] * r[l];
+            r[j] = v * L[j][j];
         }
     }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double v = s.np[i];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v -= r[j] * AN(j, i);
+        z[i] = v;
+        zz += v * v;
+    }
+    const bool dependent = !(zz > 1e-13 * s.nn) || s.amask == (1u << NV) - 1u;
+    // dual step length t1 = min u_j / r_j over r_j > 0, compared by cross-multiplication
+    double t1n = 1.0, t1d = 0.0;          // t1 = t1n / t1d, "infinite" while t1d == 0
+    int ldrop = -1;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        if (((s.amask >> j) & 1u) && r[j] > 1e-13) {
+            if (ldrop < 0 || s.u[j] * t1d < t1n * r[j]) { t1n = s.u[j]; t1d = r[j]; ldrop = j; }
+        }
+    }
+    // full step t2 = -s_p / zz
+    const bool full = !dependent && (ldrop < 0 || (-s.s_p) * t1d <= t1n * zz);
+    if (!full && ldrop < 0) { s.status = LDCBF_STATUS_INFEASIBLE; s.done = true; return; }
+    const double t = full ? (-s.s_p) / zz : t1n / t1d;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) s.u[j] -= t * r[j];
+    s.u_p += t;
+    if (!dependent) {
+#pragma unroll
+        for (int k = 1; k <= N; ++k) { s.px[k] += t * z[2 * (k - 1)]; s.py[k] += t * z[2 * (k - 1) + 1]; }
+        s.s_p += t * zz;
+    }
+    // -- slot bookkeeping: row p enters the first free slot (full step) or slot ldrop leaves (partial step)
+    const int slot = full ? first_free_slot(s.amask) : ldrop;
+    if (full) { s.amask |= 1u << slot; s.need_scan = true; }
+    else s.amask &= ~(1u << slot);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) if (j == slot) s.u[j] = full ? s.u_p : 0.0;
+    {
+        double* an = &AN(slot, 0);             // dynamic slot address
+        double* grow = &GM(slot, 0);
+        double* gcol = &GM(0, slot);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) an[i * WS] = full ? s.np[i] : 0.0;
+#pragma unroll
+        for (int l = 0; l < NV; ++l) {
+            const double val = full ? d[l] : 0.0;   // d[slot] = 0 for a free slot; the diagonal is set below
+            grow[l * WS] = val;
+            gcol[l * NV * WS] = val;
+        }
+        grow[slot * WS] = full ? s.nn : 1.0;
+    }
+}
 #undef AN
 #undef GM
 
-    // ---- outputs: states, footsteps, objective
-    S.status = status;
-    S.iters = iters;
+// Outputs: states, footsteps, objective (NaN when not solved).
+template <int N, int MO>
+LDCBF_HD void qp_finish(const StepConst& C, const QpState<N, MO>& s, QpSolution<N>& S) {
+    S.status = s.status;
+    S.iters = s.iters;
     const double nan = quiet_nan();
-    S.px[0] = p0x; S.py[0] = p0y; S.vx[0] = v0x; S.vy[0] = v0y;
-    double obj = (p0x - gx) * (p0x - gx) + (p0y - gy) * (p0y - gy);
-    const bool ok = status == LDCBF_STATUS_SOLVED;
+    const double gx = s.gx, gy = s.gy;
+#pragma unroll
+    for (int k = 0; k <= N; ++k) S.th[k] = s.th[k];
+#pragma unroll
+    for (int k = 0; k < N; ++k) S.om[k] = s.om[k];
+    S.px[0] = s.p0x; S.py[0] = s.p0y; S.vx[0] = s.v0x; S.vy[0] = s.v0y;
+    double obj = (s.p0x - gx) * (s.p0x - gx) + (s.p0y - gy) * (s.p0y - gy);
+    const bool ok = s.status == LDCBF_STATUS_SOLVED;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-        const double dx = px[k + 1] - px[k], dy = py[k + 1] - py[k];
+        const double dx = s.px[k + 1] - s.px[k], dy = s.py[k + 1] - s.py[k];
         S.vx[k + 1] = C.gtil * dx - S.vx[k];
         S.vy[k + 1] = C.gtil * dy - S.vy[k];
-        S.ux[k] = (px[k + 1] - C.ch * px[k] - C.sh_over_beta * S.vx[k]) * C.inv_one_m_ch;
-        S.uy[k] = (py[k + 1] - C.ch * py[k] - C.sh_over_beta * S.vy[k]) * C.inv_one_m_ch;
-        S.px[k + 1] = px[k + 1]; S.py[k + 1] = py[k + 1];
-        obj += (px[k + 1] - gx) * (px[k + 1] - gx) + (py[k + 1] - gy) * (py[k + 1] - gy);
+        S.ux[k] = (s.px[k + 1] - C.ch * s.px[k] - C.sh_over_beta * S.vx[k]) * C.inv_one_m_ch;
+        S.uy[k] = (s.py[k + 1] - C.ch * s.py[k] - C.sh_over_beta * S.vy[k]) * C.inv_one_m_ch;
+        S.px[k + 1] = s.px[k + 1]; S.py[k + 1] = s.py[k + 1];
+        obj += (s.px[k + 1] - gx) * (s.px[k + 1] - gx) + (s.py[k + 1] - gy) * (s.py[k + 1] - gy);
     }
     S.obj = ok ? obj : nan;
     if (!ok) {
@@ -393,6 +427,19 @@ LDCBF_HD void solve_scenario(const StepConst& C, double p0x, double v0x, double 
             S.px[k + 1] = nan; S.py[k + 1] = nan; S.vx[k + 1] = nan; S.vy[k + 1] = nan;
         }
     }
+}
+
+// One scenario from start to end (one thread).
+template <int N, int MO, int WS>
+LDCBF_HD void solve_scenario(const StepConst& C, double p0x, double v0x, double p0y, double v0y, double th0, double gx,
+                             double gy, const int (&ft)[N + 1], const double4 (&ce)[MO], int nb, double delta,
+                             double alpha_over_pi, double vmax0, double omega_max, double omega_min, double* ws,
+                             QpSolution<N>& S) {
+    QpState<N, MO> s;
+    qp_setup<N, MO, WS>(C, p0x, v0x, p0y, v0y, th0, gx, gy, ft, ce, nb, delta, alpha_over_pi, vmax0, omega_max,
+                        omega_min, ws, s);
+    while (!s.done) qp_trip<N, MO, WS>(C, ws, s);
+    qp_finish<N, MO>(C, s, S);
 }
 
 }  // namespace ldcbf

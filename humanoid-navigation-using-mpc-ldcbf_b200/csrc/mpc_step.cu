@@ -4,6 +4,13 @@
 
 #include "mpc_qp.cuh"
 
+#ifndef LDCBF_QP_REFILL_TRIPS
+#define LDCBF_QP_REFILL_TRIPS 1
+#endif
+#ifndef LDCBF_QP_REFILL_MIN_IDLE
+#define LDCBF_QP_REFILL_MIN_IDLE 8
+#endif
+
 namespace ldcbf {
 
 static thread_local cudaError_t g_last_error = cudaSuccess;
@@ -70,6 +77,70 @@ __global__ void __launch_bounds__(BLOCK) mpc_qp_kernel(StepConst C, int B, int m
     store_solution<N>(S, b, io.U, io.X, io.theta, io.omega, io.obj, io.status, io.iters);
 }
 
+// Large-batch variant: persistent warps with lane refill.  A warp of the plain kernel runs until its slowest lane
+// has converged (mean 14.8 trips, maximum over 32 lanes ~30: 14 of 32 lanes active on average, ncu).  Here every
+// warp owns a contiguous chunk of scenarios; a lane that has converged stores its result and takes the next
+// scenario of the chunk while the other lanes keep iterating, TRIPS trips between two refill points.  No global
+// counter, no atomics: the chunk cursor is warp-uniform and lanes rank themselves with a ballot.
+constexpr int REFILL_MIN_IDLE = LDCBF_QP_REFILL_MIN_IDLE;
+
+template <int N, int MO, int BLOCK, int TRIPS>
+__global__ void __launch_bounds__(BLOCK) mpc_qp_refill_kernel(StepConst C, int B, int max_obs, int per_warp, StepIO io) {
+    extern __shared__ double qp_ws[];
+    double* ws = qp_ws + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const int warp = (blockIdx.x * BLOCK + threadIdx.x) >> 5;
+    long long first = (long long)warp * per_warp;
+    int next = first < B ? (int)first : B;                       // warp-uniform chunk cursor
+    const int end = min(B, next + per_warp);
+    QpState<N, MO> s;
+    s.done = true;
+    int b = -1;                                                  // scenario this lane is working on
+    for (;;) {
+        const unsigned done_m = __ballot_sync(0xffffffffu, b >= 0 && s.done);    // converged, not yet retired
+        const unsigned idle_m = __ballot_sync(0xffffffffu, b < 0);
+        const bool none_busy = (done_m | idle_m) == 0xffffffffu;
+        const bool more = next < end;
+        // service point: retire converged lanes and refill free lanes in one (divergent) region, entered only when
+        // enough lanes are free to amortise it, or when no lane has anything left to iterate on
+        if ((more && __popc(done_m) + __popc(idle_m) >= REFILL_MIN_IDLE) || none_busy) {
+            if (b >= 0 && s.done) {
+                QpSolution<N> S;
+                qp_finish<N, MO>(C, s, S);
+                store_solution<N>(S, b, io.U, io.X, io.theta, io.omega, io.obj, io.status, io.iters);
+                b = -1;
+            }
+            if (more) {
+                const unsigned free_m = __ballot_sync(0xffffffffu, b < 0);
+                const int cand = next + __popc(free_m & ((1u << lane) - 1u));
+                if (b < 0 && cand < end) {
+                    b = cand;
+                    const double4 x = reinterpret_cast<const double4*>(io.x0)[b];
+                    const double2 g = reinterpret_cast<const double2*>(io.goal)[b];
+                    int ft[N + 1];
+#pragma unroll
+                    for (int k = 0; k <= N; ++k) ft[k] = io.foot[(size_t)b * (N + 1) + k];
+                    double aop, vmax0, omax, omin;
+                    load_limits(C, io.limits, b, aop, vmax0, omax, omin);
+                    const int nb = min(io.nobs[b], MO);
+                    double4 ce[MO];
+                    const double4* gce = reinterpret_cast<const double4*>(io.c_eta) + (size_t)b * max_obs;
+#pragma unroll
+                    for (int o = 0; o < MO; ++o) ce[o] = (o < nb) ? gce[o] : make_double4(0.0, 0.0, 0.0, 0.0);
+                    qp_setup<N, MO, BLOCK>(C, x.x, x.y, x.z, x.w, io.theta0[b], g.x, g.y, ft, ce, nb,
+                                           io.delta ? io.delta[b] : 0.0, aop, vmax0, omax, omin, ws, s);
+                }
+                next = min(end, next + __popc(free_m));
+            }
+        }
+        if (__ballot_sync(0xffffffffu, b >= 0) == 0u) break;
+#pragma unroll 1
+        for (int t = 0; t < TRIPS; ++t) {
+            if (b >= 0 && !s.done) qp_trip<N, MO, BLOCK>(C, ws, s);
+        }
+    }
+}
+
 template <int N, int MO, int BLOCK>
 static int launch_qp_block(const StepConst& C, int B, int max_obs, const StepIO& io, cudaStream_t st) {
     const size_t smem = (size_t)QpWorkspace<N>::DOUBLES * sizeof(double) * BLOCK;
@@ -87,6 +158,18 @@ static int launch_qp(const StepConst& C, int B, int max_obs, const StepIO& io, c
     // Large batches: 128-thread blocks.  Small batches leave SM sub-partitions idle, so the scenarios are spread
     // over more, narrower warps (8 lanes used per warp): a warp runs until its slowest lane has converged, and the
     // expected maximum iteration count over 8 scenarios is well below that over 32.
+    if (B >= 148 * 2 * 128 * 4) {
+        // persistent grid: 2 blocks of 128 threads per SM (register-limited occupancy), >= 128 scenarios per warp
+        constexpr int BLOCK = 128, TRIPS = LDCBF_QP_REFILL_TRIPS;
+        const int warps = 148 * 2 * (BLOCK / 32);
+        const int per_warp = (B + warps - 1) / warps;
+        const size_t smem = (size_t)QpWorkspace<N>::DOUBLES * sizeof(double) * BLOCK;
+        auto kern = mpc_qp_refill_kernel<N, MO, BLOCK, TRIPS>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_last_error(e); return LDCBF_E_LAUNCH; }
+        kern<<<148 * 2, BLOCK, smem, st>>>(C, B, max_obs, per_warp, io);
+        return check_launch();
+    }
     if (B >= 148 * 4 * 128) return launch_qp_block<N, MO, 128>(C, B, max_obs, io, st);
     if (B >= 148 * 4 * 16) return launch_qp_block<N, MO, 32>(C, B, max_obs, io, st);
     return launch_qp_block<N, MO, 8>(C, B, max_obs, io, st);

@@ -131,6 +131,69 @@ def test_mpc_step_matches_oracle_on_config2_scenarios(L):
     assert _compare(out, ref, nobs, foots, deltas) > 200
 
 
+@pytest.mark.parametrize("N", (1, 2, 4))
+def test_other_horizons_match_oracle(L, N):
+    """N_horizon is a constructor argument of the reference (maze runs use N=2, simulation_maze.py:33)."""
+    from ldcbf_b200 import scenarios
+    sc = scenarios.config2(96, seed=20 + N)
+    foots = scenarios.foot_window(sc["right_first"], 0, N)
+    verts, nverts, nobs = sc["verts"], sc["nverts"], sc["nobs"]
+    prm = L.default_params(0.4)
+    out = L.mpc_step(prm, cu(sc["state"][:, :4]), cu(sc["state"][:, 4]), cu(sc["goal"]), cu(foots, torch.int8), cu(verts),
+                     cu(nverts, torch.int32), cu(nobs, torch.int32))
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    n_ok = 0
+    for b in range(96):
+        r = mpc.mpc_step(sc["state"][b], sc["goal"][b], sc["rings"][b], [int(v) for v in foots[b]], N=N, sampling_time=0.4)
+        assert out["status"][b] == r["status"]
+        if r["status"] == 0:
+            n_ok += 1
+            assert np.abs(out["U"][b] - r["U"]).max() <= TOL_M and np.abs(out["X"][b] - r["X"]).max() <= TOL_M
+            assert abs(out["obj"][b] - r["obj"]) <= TOL_OBJ * abs(r["obj"])
+    assert n_ok > 80
+
+
+def test_many_obstacles_and_per_scenario_limits(L):
+    """8 obstacles (the MO = 8 instantiation), ragged obstacle counts incl. zero, and per-scenario ALPHA / V_MAX /
+    OMEGA overrides (bounds_tuning.py:22-26 mutates these between runs)."""
+    from ldcbf_b200 import scenarios
+    rs = np.random.default_rng(5)
+    B = 64
+    rings_all, states, goals = [], [], []
+    for b in range(B):
+        n = int(rs.integers(0, 9))
+        rings = []
+        for i in range(n):
+            c = np.array([1.5 + 1.2 * (i % 4), -1.5 + 2.2 * (i // 4)]) + rs.uniform(-0.2, 0.2, 2)
+            rings.append(scenarios.circle_ring(int(rs.integers(4, 12)), 0.3, c))
+        rings_all.append(rings)
+        states.append([-0.5, 0, rs.uniform(-2, 2), 0, rs.uniform(-1, 1)])
+        goals.append([7.0, rs.uniform(-2, 2)])
+    states, goals = np.array(states), np.array(goals)
+    foots = scenarios.foot_window(np.ones(B, bool), 0, 3)
+    verts, nverts, nobs = scenarios.pack_rings(rings_all, 8, 11)
+    limits = np.full((B, 4), np.nan)
+    limits[::2] = np.column_stack((rs.uniform(1.0, 4.0, B // 2), rs.uniform(0.5, 0.9, B // 2),
+                                   rs.uniform(0.2, 0.6, B // 2), -rs.uniform(0.2, 0.6, B // 2)))
+    prm = L.default_params(0.4)
+    out = L.mpc_step(prm, cu(states[:, :4]), cu(states[:, 4]), cu(goals), cu(foots, torch.int8), cu(verts),
+                     cu(nverts, torch.int32), cu(nobs, torch.int32), limits=cu(limits))
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    n_ok = 0
+    for b in range(B):
+        conf = model.default_conf()
+        if b % 2 == 0:
+            conf["ALPHA"], conf["V_MAX"], conf["OMEGA_MAX"], conf["OMEGA_MIN"] = (limits[b, 0], [limits[b, 1], 0.4],
+                                                                                  limits[b, 2], limits[b, 3])
+        r = mpc.mpc_step(states[b], goals[b], rings_all[b], [int(v) for v in foots[b]], sampling_time=0.4, conf=conf)
+        assert out["status"][b] == r["status"], b
+        if r["status"] == 0:
+            n_ok += 1
+            assert np.abs(out["U"][b] - r["U"]).max() <= TOL_M, b
+            assert abs(out["obj"][b] - r["obj"]) <= TOL_OBJ * abs(r["obj"])
+    assert n_ok > 40
+
+
 def test_infeasible_and_degenerate_status(L):
     geo = helpers.load_geo()
     rings = helpers.map_rings(geo, "circles")
