@@ -268,7 +268,7 @@ def run_ours(args):
             peak_fp64 = max(L.probe_fp64() for _ in range(3))
             flops = float((iters * FLOP_PER_ITER + FLOP_SETUP).sum().item())
             ach = flops / (statistics.mean(t_qp) * 1e-3) / 1e12
-            line["roofline"] = {"bound": "fp64", "kernel": "mpc_qp_kernel<3,4>", "achieved": ach, "peak": peak_fp64,
+            line["roofline"] = {"bound": "fp64", "kernel": "mpc_qp_kernel<3,4,8>", "achieved": ach, "peak": peak_fp64,
                                 "unit": "TFLOP/s", "frac": ach / peak_fp64, "traffic": profile_traffic(B),
                                 "kernel_ms": statistics.mean(t_qp),
                                 "peak_source": "FP64 FMA-chain probe measured in this run (MEASURED_PEAKS.json has no fp64 entry)",
@@ -276,11 +276,16 @@ def run_ours(args):
                                         "shows the same kernel with the GPU full"}
             # ---- large batch: the regime where the GPU is full
             line["large_batch"] = large_batch(L, sc, foots, prm, flush, peak_fp64, torch)
+            # ---- the other rows of the hot path: closed-loop rollout kernel, LiDAR caster, single-scenario latency
+            line["rollout"] = rollout_bench(L, sc, torch)
+            line["lidar"] = lidar_bench(L, flush, peak_fp64, torch)
+            line["latency_b1"] = latency_b1(L, torch)
     if rank == 0:
         line["clocks"] = clk.summary()
         if port is not None:
             cores = port.cores
-            r0, _, _ = port.rate(sc, foots, cores * 16)              # calibration
+            port.rate(sc, foots, cores * 8)                          # warm the workers (imports)
+            r0, _, _ = port.rate(sc, foots, cores * 64)              # calibration
             n_sample = int(max(cores * 64, min(r0 * 15.0, 2e6)))    # about 15 s of CPU work
             rate, n, wall = port.rate(sc, foots, n_sample)
             port.close()
@@ -329,12 +334,86 @@ def large_batch(L, sc, foots, prm, flush, peak_fp64, torch, B=1 << 20):
     hbm_src = "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     gbs_k1 = BYTES_K1 * Bl / (statistics.mean(t_hp) * 1e-3) / 1e9
     return {"batch": Bl, "value": Bl / (statistics.mean(ts) * 1e-3), "unit": UNIT, "ms_per_step": statistics.mean(ts),
-            "roofline": {"bound": "fp64", "kernel": "mpc_qp_kernel<3,4>", "achieved": ach, "peak": peak_fp64,
+            "roofline": {"bound": "fp64", "kernel": "mpc_qp_refill_kernel<3,4,128>", "achieved": ach, "peak": peak_fp64,
                          "unit": "TFLOP/s", "frac": ach / peak_fp64, "kernel_ms": statistics.mean(t_qp),
                          "traffic": profile_traffic(Bl)},
-            "roofline_hbm": {"bound": "hbm", "kernel": "halfplane_kernel<32>", "achieved": gbs_k1, "peak": hbm_peak,
+            "roofline_hbm": {"bound": "hbm", "kernel": "halfplane_kernel<exact>", "achieved": gbs_k1, "peak": hbm_peak,
                              "unit": "GB/s", "frac": gbs_k1 / hbm_peak, "kernel_ms": statistics.mean(t_hp),
                              "peak_source": hbm_src}}
+
+
+def rollout_bench(L, sc, torch, T=150):
+    """Config 2 as SURVEY.md §8d states it: closed loop to the 0.05 stop or 150 steps, one kernel launch."""
+    B = len(sc["state"])
+    eng = L.BatchedHumanoidMPC(sc["goal"], sc["verts"], sc["nverts"], sc["nobs"], N_horizon=N_HORIZON, sampling_time=0.4)
+    rf = torch.as_tensor(sc["right_first"].astype(np.int8)).cuda()
+    st0 = torch.as_tensor(sc["state"], dtype=torch.float64).cuda()
+    for _ in range(2):
+        r = eng.rollout(st0.clone(), rf, T, record=False)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        st = st0.clone()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = eng.rollout(st, rf, T, record=False)
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    solves = int(r["total_solves"].item())
+    ms = statistics.median(ts)
+    return {"batch": B, "max_steps": T, "solves": solves, "ms": ms, "value": solves / (ms * 1e-3), "unit": UNIT,
+            "us_per_step_of_batch": 1e3 * ms / max(1, int(r["steps"].max().item())),
+            "reached_stop": int((r["status"] == 0).sum().item())}
+
+
+def lidar_bench(L, flush, peak_fp64, torch, B=16384):
+    """Config 3 shape: 360 rays x 20 convex obstacles (~85 edges), lidar_range 1.5 (simulation_1.py:201-231)."""
+    from ldcbf_b200 import scenarios
+    c3 = scenarios.config3(B, seed=0)
+    cu = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).cuda()
+    pos, v = cu(c3["pos"], torch.float64), cu(c3["verts"], torch.float64)
+    nv, no = cu(c3["nverts"], torch.int32), cu(c3["nobs"], torch.int32)
+    rays = L.binding.ray_table(1.5, 360).cuda()
+    fn = lambda: L.lidar_cast(pos, v, nv, no, 1.5, 360, rays=rays)
+    for _ in range(3):
+        ho, he, xy = fn()
+    torch.cuda.synchronize()
+    ts = timed_steps(fn, 10, flush, torch)
+    ms = statistics.mean(ts)
+    edges = float(c3["nverts"].sum())
+    flops = 30.0 * 360 * edges                      # ~30 flop per ray-edge test (SURVEY.md §8d)
+    ach = flops / (ms * 1e-3) / 1e12
+    return {"batch": B, "rays": 360, "mean_edges": edges / B, "ms": ms, "scans_per_s": B / (ms * 1e-3),
+            "hit_fraction": float((ho >= 0).float().mean().item()),
+            "roofline": {"bound": "fp64", "kernel": "lidar_kernel", "achieved": ach, "peak": peak_fp64,
+                         "unit": "TFLOP/s", "frac": ach / peak_fp64}}
+
+
+def latency_b1(L, torch, n=200):
+    """p50 latency of one MPC step for ONE scenario (config 1: the reference's basic simulation), device-resident
+    inputs, one call of ldcbf_mpc_step_f64 + a stream synchronise."""
+    from ldcbf_b200 import scenarios
+    rings = scenarios.circle_rings()
+    verts, nverts, nobs = scenarios.pack_rings([rings])
+    cu = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).cuda()
+    x0, th, g = cu([[0.0, 0, 3, 0]]), cu([0.0]), cu([[6.0, -3.0]])
+    ft, v, nv, no = cu([[1, -1, 1, -1]], torch.int8), cu(verts), cu(nverts, torch.int32), cu(nobs, torch.int32)
+    prm = L.default_params(0.4)
+    out = {}
+    ts, tw = [], []
+    for i in range(n + 20):
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.mpc_step(prm, x0, th, g, ft, v, nv, no, out=out)
+        e1.record()
+        e1.synchronize()
+        if i >= 20:
+            ts.append(e0.elapsed_time(e1) * 1e3)
+            tw.append((time.perf_counter() - t0) * 1e6)
+    return {"p50_device_us": statistics.median(ts), "p50_wall_us": statistics.median(tw),
+            "note": "B=1, config 1 step 0; reference: CasADi/IPOPT per step, not measurable offline"}
 
 
 def e2e(L, sc, foots, args, torch):

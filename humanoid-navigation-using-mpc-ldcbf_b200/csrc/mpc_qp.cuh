@@ -193,7 +193,7 @@ LDCBF_HD void qp_setup(const StepConst& C, double p0x, double v0x, double p0y, d
     int status = LDCBF_STATUS_SOLVED;
 #pragma unroll
     for (int o = 0; o < MO; ++o) {
-        s.ex[o] = 0.0; s.ey[o] = 0.0; s.hb[o] = -1.0;
+        s.ex[o] = 0.0; s.ey[o] = 0.0; s.hb[o] = -INFINITY;    // absent obstacle: slack 0*p - (-inf) = +inf, never chosen
         if (o < nb) {
             s.ex[o] = ce[o].z; s.ey[o] = ce[o].w;
             s.hb[o] = ce[o].z * ce[o].x + ce[o].w * ce[o].y + delta;
@@ -271,7 +271,7 @@ LDCBF_HD void qp_trip(const StepConst& C, double* ws, QpState<N, MO>& s) {
                 upper |= nonneg_bit(m) << (2 * N + 2 * k + 1);
 #pragma unroll
                 for (int o = 0; o < MO; ++o)
-                    sl[4 * N + k * MO + o] = (o < s.nb) ? s.ex[o] * s.px[kk] + s.ey[o] * s.py[kk] - s.hb[o] : INFINITY;
+                    sl[4 * N + k * MO + o] = s.ex[o] * s.px[kk] + s.ey[o] * s.py[kk] - s.hb[o];
             }
         }
         // tournament argmin: (value, index) pairs, one compare and three selects per node

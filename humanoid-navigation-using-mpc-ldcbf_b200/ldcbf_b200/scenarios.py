@@ -98,3 +98,37 @@ def foot_window(right_first, step, N):
     even = (idx % 2) == 0
     s = np.where(even == right_first[:, None], 1, -1)
     return s.astype(np.int8)
+
+
+def config3(B=16384, seed=0, pool=64, n_obstacles=20):
+    """Unknown-environment shape (`report_simulations/simulation_1.py:201-231`): start (0,0)
+    heading pi/2, goal (4, 3.5), `n_obstacles` convex polygons = hull of 5 uniform points in a 1x1 box around centres
+    drawn in (-1,6)^2, rejecting a candidate whose box comes within 0.2 of an accepted box or that contains the start
+    or the goal (a simplification of the rejection rules of `Utils/obstacles.py:167-194` with the same obstacle
+    density).  `pool` distinct maps are generated and tiled to B scenarios; the LiDAR pose is jittered per scenario.
+    Returns dict(state[B,5], goal[B,2], verts[B,20,5,2], nverts, nobs, rings (pool lists), pos[B,2])."""
+    from scipy.spatial import ConvexHull
+    rng = np.random.default_rng(seed)
+    maps = []
+    for _ in range(pool):
+        rings, centres = [], []
+        tries = 0
+        while len(rings) < n_obstacles and tries < 400:
+            tries += 1
+            c = rng.uniform(-1, 6, 2)
+            if any(np.max(np.abs(c - q)) < 1.2 for q in centres):
+                continue
+            pts = c + rng.uniform(-0.5, 0.5, (5, 2))
+            ring = pts[ConvexHull(pts).vertices]
+            if any(_inside_convex(np.array(q), ring) or _dist_to_ring(np.array(q), ring) < 0.1 for q in ((0.0, 0.0), (4.0, 3.5))):
+                continue
+            rings.append(ring)
+            centres.append(c)
+        maps.append(rings)
+    verts_p, nverts_p, nobs_p = pack_rings(maps, n_obstacles, 5)
+    idx = np.arange(B) % pool
+    pos = np.column_stack((rng.uniform(-0.2, 4.2, B), rng.uniform(-0.2, 3.7, B)))
+    state = np.zeros((B, 5))
+    state[:, 0], state[:, 2], state[:, 4] = pos[:, 0], pos[:, 1], math.pi / 2
+    return dict(state=state, goal=np.tile([4.0, 3.5], (B, 1)), verts=verts_p[idx], nverts=nverts_p[idx], nobs=nobs_p[idx],
+                rings=maps, map_index=idx, pos=pos)
