@@ -57,9 +57,19 @@ __global__ void __launch_bounds__(128) lidar_kernel(int R, const double2* __rest
             const double wx = __dsub_rn(a1x, A.x), wy = __dsub_rn(a1y, A.y);           // a1 - a2
             const double denom = __dsub_rn(__dmul_rn(e2y, d1x), __dmul_rn(e2x, d1y));
             if (denom != 0.0) {
-                const double ua = __ddiv_rn(__dsub_rn(__dmul_rn(e2x, wy), __dmul_rn(e2y, wx)), denom);
-                const double ub = __ddiv_rn(__dsub_rn(__dmul_rn(d1x, wy), __dmul_rn(d1y, wx)), denom);
-                if (ua >= 0.0 && ua <= 1.0 && ub >= 0.0 && ub <= 1.0) {
+                // 0 <= ua <= 1 and 0 <= ub <= 1 decided WITHOUT the divisions: for IEEE doubles
+                //   num/denom >= 0  <=>  num == 0 or sign(num) == sign(denom)      (-0.0 >= 0 holds in Python too)
+                //   num/denom <= 1  <=>  |num| <= |denom|   (|num| > |denom| gives a quotient >= 1 + 2^-52, which
+                //                                            is representable, so rounding cannot pull it down to 1)
+                // so the two ~25-instruction divisions are only paid by the few (ray, edge) pairs that really hit.
+                const double na = __dsub_rn(__dmul_rn(e2x, wy), __dmul_rn(e2y, wx));
+                const double nb = __dsub_rn(__dmul_rn(d1x, wy), __dmul_rn(d1y, wx));
+                const double ad = fabs(denom);
+                const bool dneg = denom < 0.0;
+                const bool oka = (na == 0.0 || ((na < 0.0) == dneg)) && fabs(na) <= ad;
+                const bool okb = (nb == 0.0 || ((nb < 0.0) == dneg)) && fabs(nb) <= ad;
+                if (oka && okb) {
+                    const double ua = __ddiv_rn(na, denom);
                     const double x = __dadd_rn(a1x, __dmul_rn(ua, d1x));
                     const double y = __dadd_rn(a1y, __dmul_rn(ua, d1y));
                     const double dx = __dsub_rn(x, p.x), dy = __dsub_rn(y, p.y);
