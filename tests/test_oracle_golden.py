@@ -130,3 +130,24 @@ def test_closed_loop_reaches_goal(geo):
     assert X.shape[0] == 5 and U.shape[0] == 3 and X.shape[1] == U.shape[1] + 1
     assert 80 <= U.shape[1] <= 92          # reference: 86 steps
     assert np.hypot(X[0, -1] - 6, X[2, -1] + 3) < 0.2
+
+
+def test_pspace_oracle_equals_footstep_oracle(geo):
+    """The position-space restatement (checker for long horizons) is the same QP as the reference-shaped one."""
+    from oracle import qp_pspace
+    conf = model.default_conf()
+    rings = _circle_rings(geo)
+    g = np.load(os.path.join(G, "circles_delta_traj.npz"))
+    s_v = model.foot_parity(200, True)
+    for k in range(0, 88, 3):
+        for N in (2, 3, 4):
+            a = mpc.mpc_step(g["X"][:, k], g["goal"], rings, s_v[k:k + N + 1], N=N, sampling_time=0.4, delta=0.3)
+            b = qp_pspace.mpc_step(g["X"][:, k], g["goal"], rings, s_v[k:k + N + 1], N, 0.4, conf, delta=0.3)
+            assert a["status"] == b["status"]
+            if a["status"] == 0:
+                np.testing.assert_allclose(b["U"], a["U"], atol=2e-8)
+                np.testing.assert_allclose(b["X"], a["X"], atol=2e-8)
+                assert abs(a["obj"] - b["obj"]) < 1e-8 * a["obj"]
+    # long horizon: the footstep-space Hessian is singular in fp64, the position-space LDP still certifies
+    b = qp_pspace.mpc_step((0, 0, 3, 0, 0), (6, -3), rings, model.foot_parity(41, True), 40, 0.4, conf)
+    assert b["status"] == 0 and b["kkt"][0] < 1e-7 and b["kkt"][1] < 1e-8
