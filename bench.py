@@ -280,6 +280,7 @@ def run_ours(args):
             line["rollout"] = rollout_bench(L, sc, torch)
             line["rollout_margin_1e-6"] = rollout_bench(L, sc, torch, delta=1e-6)
             line["lidar"] = lidar_bench(L, flush, peak_fp64, torch)
+            line["unknown_env"] = unknown_env_bench(L, flush, torch)
             line["latency_b1"] = latency_b1(L, torch)
     if rank == 0:
         line["clocks"] = clk.summary()
@@ -395,6 +396,30 @@ def lidar_bench(L, flush, peak_fp64, torch, B=16384):
             "hit_fraction": float((ho >= 0).float().mean().item()),
             "roofline": {"bound": "fp64", "kernel": "lidar_kernel", "achieved": ach, "peak": peak_fp64,
                          "unit": "TFLOP/s", "frac": ach / peak_fp64}}
+
+
+def unknown_env_bench(L, flush, torch, B=16384):
+    """Config 3 end to end on the device: LiDAR scan (K4) -> clusters + hulls (f1) -> half-planes of the inferred
+    obstacles (K1) -> QP (K2+K3), noisy readings (sigma = 0.01 as range_finder `:161-172`, tensor injected)."""
+    from ldcbf_b200 import scenarios
+    c3 = scenarios.config3(B, seed=0)
+    foots = scenarios.foot_window(np.ones(B, bool), 0, N_HORIZON)
+    eng = L.BatchedUnknownEnvMPC(c3["goal"], c3["verts"], c3["nverts"], c3["nobs"], lidar_range=1.5, sampling_time=0.4,
+                                 N_horizon=N_HORIZON)
+    cu = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).cuda()
+    x0, th, ft = cu(c3["state"][:, :4], torch.float64), cu(c3["state"][:, 4], torch.float64), cu(foots, torch.int8)
+    noise = torch.randn((B, 360, 2), dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(0)) * 0.01
+    for _ in range(3):
+        out = eng.step(x0, th, ft, noise=noise)
+    torch.cuda.synchronize()
+    ts = timed_steps(lambda: eng.step(x0, th, ft, noise=noise), 10, flush, torch)
+    xy = out["sensed"]["hit_xy"]
+    t_f1 = timed_steps(lambda: L.lidar_clusters(xy, noise=noise), 10, flush, torch)
+    ms = statistics.mean(ts)
+    return {"batch": B, "ms_per_step": ms, "value": B / (ms * 1e-3), "unit": UNIT, "f1_kernel_ms": statistics.mean(t_f1),
+            "mean_inferred_obstacles": float(out["sensed"]["nobs"].double().mean().item()),
+            "overflow": int(out["sensed"]["overflow"].sum().item()),
+            "status_counts": torch.bincount(out["status"], minlength=4).tolist(), "gpu_launches_per_step": 4}
 
 
 def latency_b1(L, torch, n=200):

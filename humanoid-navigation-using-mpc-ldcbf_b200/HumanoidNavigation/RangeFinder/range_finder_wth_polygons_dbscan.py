@@ -1,30 +1,33 @@
 """Mirror of `RangeFinder/range_finder_wth_polygons_dbscan.py`.
 
-`compute_lidar_readings` (reference :26-63) runs on the GPU (K4, csrc/lidar.cu) and returns the same list of
-`(x, y)` tuples / None.  The post-processing — Gaussian noise (:161-172), DBSCAN eps=0.3 min_samples=3 (:100-116),
-convex hulls with a closing vertex (:65-83, :119-126) — is host code here (sklearn / scipy), the "next" row f1 of
-SURVEY.md §8f.
+`compute_lidar_readings` (reference :26-63) is the K4 kernel (csrc/lidar.cu); clustering and hulls
+(`retrieve_clusters` :100-116, `create_convex_hull` :65-83, `build_local_obstacles` :119-126) are the f1 kernel
+(csrc/lidar_clusters.cu).  The functions return the reference's Python shapes: readings as a list of `(x, y)` / None,
+clusters as a list of (n,2) arrays in sklearn's label order, local obstacles as closed polygons (first vertex repeated).
+The Gaussian noise of `range_finder` (:161-172) is drawn on the host from numpy's global RNG exactly like the
+reference (two normals per valid reading, in ray order) and handed to the kernel.
 """
 import numpy as np
 import torch
-from scipy.spatial import ConvexHull, QhullError
-from sklearn.cluster import DBSCAN
 
 import ldcbf_b200
+
+
+def _dev():
+    return torch.device("cuda")
 
 
 def cast(lidar_position, obstacles, lidar_range, resolution=360):
     """K4 for one pose: (hit_obs[R], hit_edge[R], hit_xy[R,2]) numpy arrays.  obstacles: list of (n,2) arrays,
     edges (i, i+1 mod n) over the rows as given (reference Utils/obstacles.py:127-134)."""
     from ldcbf_b200.scenarios import pack_rings
-    dev = torch.device("cuda")
     obstacles = [np.asarray(o, dtype=np.float64) for o in obstacles]
     if not obstacles:
         return (np.full(resolution, -1, np.int32), np.full(resolution, -1, np.int32), np.full((resolution, 2), np.nan))
     verts, nverts, nobs = pack_rings([obstacles])
-    ho, he, xy = ldcbf_b200.lidar_cast(torch.as_tensor(np.asarray(lidar_position, dtype=np.float64).reshape(1, 2), device=dev),
-                                       torch.as_tensor(verts, device=dev), torch.as_tensor(nverts, device=dev),
-                                       torch.as_tensor(nobs, device=dev), float(lidar_range), int(resolution))
+    ho, he, xy = ldcbf_b200.lidar_cast(torch.as_tensor(np.asarray(lidar_position, dtype=np.float64).reshape(1, 2), device=_dev()),
+                                       torch.as_tensor(verts, device=_dev()), torch.as_tensor(nverts, device=_dev()),
+                                       torch.as_tensor(nobs, device=_dev()), float(lidar_range), int(resolution))
     return ho[0].cpu().numpy(), he[0].cpu().numpy(), xy[0].cpu().numpy()
 
 
@@ -33,31 +36,35 @@ def compute_lidar_readings(position, obstacles, lidar_range, resolution=360):
     return [None if np.isnan(p[0]) else (float(p[0]), float(p[1])) for p in xy]
 
 
-def create_convex_hull(points):
-    points = np.unique(points, axis=0)
-    if len(points) < 3 or np.linalg.matrix_rank(points - points[0]) < 2:
-        return None
-    try:
-        return points[ConvexHull(points).vertices]
-    except QhullError:
-        return None
+def _cluster(xy, eps=0.3, min_samples=3):
+    """f1 for one scan given as an (R,2) array with NaN rows: (labels[R], hull rings list)."""
+    R = xy.shape[0]
+    out = ldcbf_b200.lidar_clusters(torch.as_tensor(np.ascontiguousarray(xy[None]), device=_dev()), eps=eps,
+                                    min_samples=min_samples, max_hulls=64, max_hull_verts=max(16, min(R, 192)))
+    labels = out["labels"][0].cpu().numpy()
+    nv = out["nverts"][0].cpu().numpy()
+    v = out["verts"][0].cpu().numpy()
+    return labels, [v[o, :nv[o]].copy() for o in range(int(out["nobs"][0].item()))]
+
+
+def _as_array(points):
+    return np.array([[np.nan, np.nan] if p is None else [p[0], p[1]] for p in points], dtype=np.float64).reshape(-1, 2)
 
 
 def retrieve_clusters(points, eps=0.3, min_samples=3):
-    pts = np.array([p for p in points if p is not None])
-    if pts.size == 0:
+    xy = _as_array(points)
+    if xy.size == 0 or np.isnan(xy[:, 0]).all():
         return []
-    pts = pts.reshape(-1, 2)
-    labels = DBSCAN(eps=eps, min_samples=min_samples).fit(pts).labels_
-    return [pts[labels == i] for i in set(labels) if i != -1]
+    labels, _ = _cluster(xy, eps, min_samples)
+    return [xy[labels == i] for i in sorted(set(labels.tolist())) if i != -1]
 
 
 def build_local_obstacles(clusters):
     out = []
     for cluster in clusters:
-        poly = create_convex_hull(cluster)
-        if poly is not None:
-            out.append(np.append(poly, [poly[0]], axis=0))
+        _, rings = _cluster(np.asarray(cluster, dtype=np.float64), eps=np.inf if False else 1e9, min_samples=1)
+        if rings:
+            out.append(np.append(rings[0], [rings[0][0]], axis=0))
     return out
 
 
@@ -72,5 +79,10 @@ def range_finder(lidar_position, obstacles, lidar_range=3.0, resolution=360, noi
             else:
                 noisy_readings.append(None)
         readings = noisy_readings
-    clusters = retrieve_clusters(readings)
-    return readings, clusters, build_local_obstacles(clusters)
+    xy = _as_array(readings)
+    if xy.size == 0 or np.isnan(xy[:, 0]).all():
+        return readings, [], []
+    labels, rings = _cluster(xy)
+    clusters = [xy[labels == i] for i in sorted(set(labels.tolist())) if i != -1]
+    local_obstacles = [np.append(r, [r[0]], axis=0) for r in rings]
+    return readings, clusters, local_obstacles

@@ -94,3 +94,36 @@ class BatchedHumanoidMPC:
         goals = self.goal[:, None, :].contiguous() if goals is None else goals
         return _b.rollout(self.prm, state, goals, right_first, self.verts, self.nverts, self.nobs, T, N=self.N,
                           max_steps_per_goal=max_steps_per_goal, delta=self.delta, limits=self.limits, record=record)
+
+
+class BatchedUnknownEnvMPC(BatchedHumanoidMPC):
+    """Unknown-environment variant, batched and entirely on the device: every step scans the true map with the LiDAR
+    caster (K4), clusters the readings and builds the convex hulls (f1), and solves the MPC step against the
+    *inferred* obstacles (K1 + K2+K3) — `HumanoidMPCUnknownEnvironment._get_list_c_and_eta` + one loop iteration of
+    the reference, for B scenarios at once.  `verts` are the true obstacles in the order the reference casts
+    against (`ConvexHull.points` rows)."""
+
+    def __init__(self, goal, verts, nverts, nobs, lidar_range=3.0, lidar_resolution=360, max_hulls=8,
+                 max_hull_verts=64, eps=0.3, min_samples=3, **kw):
+        super().__init__(goal, verts, nverts, nobs, **kw)
+        self.lidar_range = float(lidar_range)
+        self.rays = _b.ray_table(lidar_range, lidar_resolution).to(self.device)
+        self.max_hulls, self.max_hull_verts = max_hulls, max_hull_verts
+        self.eps, self.min_samples = eps, min_samples
+
+    def sense(self, pos, noise=None):
+        """pos[B,2] -> dict(hit_obs, hit_edge, hit_xy, labels, verts, nverts, nobs, overflow) (inferred obstacles)."""
+        ho, he, xy = _b.lidar_cast(pos, self.verts, self.nverts, self.nobs, self.lidar_range, rays=self.rays)
+        cl = _b.lidar_clusters(xy, noise=noise, eps=self.eps, min_samples=self.min_samples,
+                               max_hulls=self.max_hulls, max_hull_verts=self.max_hull_verts)
+        cl.update(hit_obs=ho, hit_edge=he, hit_xy=xy)
+        return cl
+
+    def step(self, x0, theta0, foot, goal=None, noise=None):
+        pos = x0[:, [0, 2]].contiguous()
+        sensed = self.sense(pos, noise)
+        self._out = _b.mpc_step(self.prm, x0, theta0, self.goal if goal is None else goal, foot, sensed["verts"],
+                                sensed["nverts"], sensed["nobs"], delta=self.delta, limits=self.limits, out=self._out)
+        out = dict(self._out)
+        out["sensed"] = sensed
+        return out

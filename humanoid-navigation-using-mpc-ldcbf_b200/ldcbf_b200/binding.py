@@ -13,6 +13,7 @@ MAX_OBSTACLES = 8      # LDCBF_MAX_OBSTACLES of include/ldcbf_mpc.h
 
 EXPORTS = ("ldcbf_abi_version", "ldcbf_params_default", "ldcbf_last_cuda_error", "ldcbf_workspace_bytes",
            "ldcbf_halfplanes_f64", "ldcbf_mpc_qp_f64", "ldcbf_mpc_step_f64", "ldcbf_lidar_cast_f64",
+           "ldcbf_lidar_clusters_f64",
            "ldcbf_rollout_f64", "ldcbf_probe_fp64_fma")
 
 
@@ -54,6 +55,7 @@ def lib():
         L.ldcbf_mpc_qp_f64.argtypes = [POINTER(LdcbfParams), c_int, c_int, c_int] + [P] * 16
         L.ldcbf_mpc_step_f64.argtypes = [POINTER(LdcbfParams), c_int, c_int, c_int, c_int] + [P] * 19
         L.ldcbf_lidar_cast_f64.argtypes = [c_int, c_int, P, c_double, P, c_int, c_int, P, P, P, P, P, P, P]
+        L.ldcbf_lidar_clusters_f64.argtypes = [c_int, c_int, P, P, c_double, c_int, c_int, c_int, P, P, P, P, P, P]
         L.ldcbf_rollout_f64.argtypes = [POINTER(LdcbfParams)] + [c_int] * 7 + [P] * 15
         L.ldcbf_probe_fp64_fma.argtypes = [c_int, c_int, c_int, P, P]
         for name in EXPORTS:
@@ -200,6 +202,23 @@ def lidar_cast(pos, verts, nverts, nobs, lidar_range, resolution=360, rays=None)
                                           _ptr(hit_obs[s:e], I32, "hit_obs"), _ptr(hit_edge[s:e], I32, "hit_edge"),
                                           _ptr(hit_xy[s:e], F64, "hit_xy"), _stream()), "ldcbf_lidar_cast_f64")
     return hit_obs, hit_edge, hit_xy
+
+
+def lidar_clusters(hit_xy, noise=None, eps=0.3, min_samples=3, max_hulls=MAX_OBSTACLES, max_hull_verts=16):
+    """f1.  hit_xy[B,R,2] (NaN = no reading) -> dict(labels[B,R], verts[B,max_hulls,max_hull_verts,2], nverts, nobs,
+    overflow[B]); verts/nverts/nobs feed `half_planes` / `mpc_step` directly."""
+    B, R = hit_xy.shape[0], hit_xy.shape[1]
+    dev = hit_xy.device
+    labels = torch.empty((B, R), dtype=I32, device=dev)
+    verts = torch.empty((B, max_hulls, max_hull_verts, 2), dtype=F64, device=dev)
+    nverts = torch.empty((B, max_hulls), dtype=I32, device=dev)
+    nobs = torch.empty((B,), dtype=I32, device=dev)
+    overflow = torch.empty((B,), dtype=I32, device=dev)
+    _check(lib().ldcbf_lidar_clusters_f64(B, R, _ptr(hit_xy, F64, "hit_xy"), _ptr(noise, F64, "noise"), float(eps),
+                                          int(min_samples), max_hulls, max_hull_verts, _ptr(labels, I32, "labels"),
+                                          _ptr(verts, F64, "verts"), _ptr(nverts, I32, "nverts"), _ptr(nobs, I32, "nobs"),
+                                          _ptr(overflow, I32, "overflow"), _stream()), "ldcbf_lidar_clusters_f64")
+    return dict(labels=labels, verts=verts, nverts=nverts, nobs=nobs, overflow=overflow)
 
 
 def rollout(prm, state, goals, right_first, verts, nverts, nobs, T, N=3, max_steps_per_goal=None, delta=None,

@@ -125,6 +125,21 @@ int ldcbf_lidar_cast_f64(int B, int R, const double* ray_dirs, double lidar_rang
                          int max_verts, const double* verts, const int32_t* nverts, const int32_t* nobs,
                          int32_t* hit_obs, int32_t* hit_edge, double* hit_xy, void* cuda_stream);
 
+/* f1 — LiDAR post-processing: clustering and convex hulls of the clusters, one scan per scenario.
+ * Replaces retrieve_clusters (sklearn DBSCAN, eps = 0.3, min_samples = 3), create_convex_hull and build_local_obstacles
+ * (RangeFinder/range_finder_wth_polygons_dbscan.py:65-126) and the Gaussian-noise step (:161-172; the noise is an
+ * input tensor because the reference draws it from the unseeded global numpy RNG).
+ *   hit_xy [B,R,2] readings (NaN = none), R <= 512;  noise [B,R,2] or NULL
+ * out: labels [B,R] int32   cluster number per ray in sklearn's label order, -1 = noise / no reading
+ *      hull_verts [B,max_hulls,max_hull_verts,2]  hull vertices, counter-clockwise, no closing vertex, zero padded
+ *      hull_nverts [B,max_hulls], n_hulls [B]     clusters the reference discards (< 3 distinct points, collinear)
+ *                                                 produce no hull; hulls keep the cluster order
+ *      overflow [B] or NULL                       1 when a scan had more hulls / vertices than the buffers hold
+ * The outputs have the layout of the verts / nverts / nobs inputs of ldcbf_halfplanes_f64 and ldcbf_mpc_step_f64. */
+int ldcbf_lidar_clusters_f64(int B, int R, const double* hit_xy, const double* noise, double eps, int min_samples,
+                             int max_hulls, int max_hull_verts, int32_t* labels, double* hull_verts,
+                             int32_t* hull_nverts, int32_t* n_hulls, int32_t* overflow, void* cuda_stream);
+
 /* Closed loop (HumanoidMpc.py:380-459, incl. the mpc_step = int(DELTA_T/sampling_time) sub-stepping of :74-78,
  * :384,:443-446) with optional sub-goal sequencing (HumanoidMPCVariants/HumanoidMPCWithRRT.py:153-181: a fresh
  * run per sub-goal — objective memory and foot parity restart, the state carries over).  One kernel launch.

@@ -151,3 +151,23 @@ def test_pspace_oracle_equals_footstep_oracle(geo):
     # long horizon: the footstep-space Hessian is singular in fp64, the position-space LDP still certifies
     b = qp_pspace.mpc_step((0, 0, 3, 0, 0), (6, -3), rings, model.foot_parity(41, True), 40, 0.4, conf)
     assert b["status"] == 0 and b["kkt"][0] < 1e-7 and b["kkt"][1] < 1e-8
+
+
+def test_dbscan_restatement_equals_sklearn(geo, lid):
+    """The numpy restatement of DBSCAN (what the device kernel implements) gives sklearn's labels on LiDAR scans."""
+    from sklearn.cluster import DBSCAN
+    from oracle import range_finder
+    rs = np.random.default_rng(3)
+    n = 0
+    for name in MAPS:
+        for rn in ("r15", "r30"):
+            for reads in lid[f"{name}/{rn}/readings"][:6]:
+                for sigma in (0.0, 0.01):
+                    pts = reads[~np.isnan(reads[:, 0])]
+                    if len(pts) == 0:
+                        continue
+                    pts = pts + rs.normal(0, sigma, pts.shape) if sigma else pts
+                    ref = DBSCAN(eps=0.3, min_samples=3).fit(pts).labels_
+                    assert np.array_equal(range_finder.dbscan_labels(pts), ref)
+                    n += 1
+    assert n > 40
