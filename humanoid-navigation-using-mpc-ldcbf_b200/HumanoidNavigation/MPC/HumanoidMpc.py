@@ -82,7 +82,7 @@ class HumanoidMPC:
         """One K2+K3 launch for this scenario given the half-planes."""
         n = len(list_c)
         t = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=self._dev)
-        ce = np.zeros((1, max(n, 1), 4))
+        ce = np.zeros((1, max(n, 1), 4))                 # any number of obstacles: 8 in registers, the rest streamed
         for o in range(n):
             ce[0, o, :2] = np.asarray(list_c[o]).ravel()
             ce[0, o, 2:] = np.asarray(list_eta[o]).ravel()

@@ -104,18 +104,23 @@ struct QpSolution {
 template <int N, int MO>
 LDCBF_HD void row_normal(int id, double sg, double gtil, const double (&rc)[N + 1],
                                            const double (&rs)[N + 1], const int (&ft)[N + 1],
-                                           const double (&ex)[MO], const double (&ey)[MO], double (&a)[2 * N]) {
+                                           const double (&ex)[MO], const double (&ey)[MO], const double4* ces, int ns,
+                                           double (&a)[2 * N]) {
     // decode without dynamic register indexing: select chains over the (static) k and o
-    int typ, k, sub;   // typ 0 leg, 1 vel, 2 cbf; k = state index the row "ends" at (1..N)
+    int typ, k, sub;   // typ 0 leg, 1 vel, 2 cbf (registers), 3 cbf (streamed); k = state index the row "ends" at
     if (id < 2 * N) { typ = 0; k = (id >> 1) + 1; sub = id & 1; }
     else if (id < 4 * N) { typ = 1; k = ((id - 2 * N) >> 1) + 1; sub = id & 1; }
-    else { typ = 2; k = (id - 4 * N) / MO + 1; sub = (id - 4 * N) - (k - 1) * MO; }
+    else if (id < 4 * N + N * MO) { typ = 2; k = (id - 4 * N) / MO + 1; sub = (id - 4 * N) - (k - 1) * MO; }
+    else { typ = 3; const int j = id - (4 * N + N * MO); k = j / ns + 1; sub = j - (k - 1) * ns; }
     const int kth = (typ == 0) ? k - 1 : k;     // heading index used by the row
     double c = 0.0, s = 0.0, f = 1.0;
 #pragma unroll
     for (int j = 0; j <= N; ++j) if (j == kth) { c = rc[j]; s = rs[j]; f = (double)ft[j]; }
     double rx, ry;
-    if (typ == 2) {
+    if (typ == 3) {
+        const double4 ce = ces[sub];
+        rx = ce.z; ry = ce.w;
+    } else if (typ == 2) {
         rx = 0.0; ry = 0.0;
 #pragma unroll
         for (int o = 0; o < MO; ++o) if (o == sub) { rx = ex[o]; ry = ey[o]; }
@@ -130,7 +135,7 @@ LDCBF_HD void row_normal(int id, double sg, double gtil, const double (&rc)[N + 
         else if (d > 0) {
             if (typ == 0) kap = (d == 1) ? -1.0 : 0.0;
             else if (typ == 1) kap = (d & 1) ? -2.0 * gtil : 2.0 * gtil;
-        }
+        }   // typ 2, 3: only the row's own state
         a[2 * i] = kap * rx; a[2 * i + 1] = kap * ry;
     }
 }
@@ -148,8 +153,11 @@ struct QpState {
     double rc[N + 1], rs[N + 1];          // cos / sin of the heading schedule
     double th[N + 1], om[N];
     int ft[N + 1];                        // foot parity window
-    double ex[MO], ey[MO], hb[MO];        // half-planes: eta . p >= hb
+    double ex[MO], ey[MO], hb[MO];        // half-planes of the first MO obstacles, in registers: eta . p >= hb
     int nb;
+    const double4* ces;                   // obstacles beyond MO are streamed from global memory (c, eta) per scan
+    int ns;                               // how many of them
+    double delta;
     double vmid[N + 1], vhalf[N + 1];     // merged longitudinal velocity row at state k: mid +- half
     double p0x, p0y, v0x, v0y, gx, gy;
     double px[N + 1], py[N + 1];          // current iterate w = (p_1..p_N), p_0 fixed
@@ -167,11 +175,12 @@ struct QpState {
 // ce[o] = (c_x, c_y, eta_x, eta_y) for o < nb.
 template <int N, int MO, int WS>
 LDCBF_HD void qp_setup(const StepConst& C, double p0x, double v0x, double p0y, double v0y, double th0, double gx,
-                       double gy, const int (&ft)[N + 1], const double4 (&ce)[MO], int nb, double delta,
-                       double alpha_over_pi, double vmax0, double omega_max, double omega_min, double* ws,
-                       QpState<N, MO>& s) {
+                       double gy, const int (&ft)[N + 1], const double4 (&ce)[MO], int nb, const double4* ce_stream,
+                       int n_stream, double delta, double alpha_over_pi, double vmax0, double omega_max,
+                       double omega_min, double* ws, QpState<N, MO>& s) {
     constexpr int NV = 2 * N;
     s.p0x = p0x; s.p0y = p0y; s.v0x = v0x; s.v0y = v0y; s.gx = gx; s.gy = gy; s.nb = nb;
+    s.ces = ce_stream; s.ns = n_stream; s.delta = delta;
 #pragma unroll
     for (int k = 0; k <= N; ++k) s.ft[k] = ft[k];
     // ---- heading schedule (HumanoidMpc.py:137-160)
@@ -201,6 +210,12 @@ LDCBF_HD void qp_setup(const StepConst& C, double p0x, double v0x, double p0y, d
             // constant k = 0 row (HumanoidMpc.py:284-292 with k = 0)
             else if (s.ex[o] * p0x + s.ey[o] * p0y - s.hb[o] < -C.eps_const_row) status = LDCBF_STATUS_INFEASIBLE;
         }
+    }
+    for (int o = 0; o < n_stream; ++o) {      // streamed obstacles: same two checks
+        const double4 c4 = ce_stream[o];
+        if (!(c4.z == c4.z) || !(c4.w == c4.w)) status = LDCBF_STATUS_DEGENERATE;
+        else if (c4.z * (p0x - c4.x) + c4.w * (p0y - c4.y) - delta < -C.eps_const_row && status == LDCBF_STATUS_SOLVED)
+            status = LDCBF_STATUS_INFEASIBLE;
     }
     // merged longitudinal velocity row at state k: [V_MIN0, min(V_MAX0, V_MAX0 - alpha/pi |omega_{k-1}|)]
     s.vmid[0] = 0.0; s.vhalf[0] = 0.0;
@@ -287,11 +302,21 @@ LDCBF_HD void qp_trip(const StepConst& C, double* ws, QpState<N, MO>& s) {
                 ti[i] = take ? ti[n - 1 - i] : ti[i];
             }
         }
-        const double best = sl[0];
+        double best = sl[0];
+        int bid = ti[0];
+        // obstacles beyond the register-resident MO: one streaming pass over (c, eta) in global memory (L1/L2)
+        for (int o = 0; o < s.ns; ++o) {
+            const double4 c4 = s.ces[o];
+            const double hbo = c4.z * c4.x + c4.w * c4.y + s.delta;
+#pragma unroll
+            for (int k = 1; k <= N; ++k) {
+                const double v = c4.z * s.px[k] + c4.w * s.py[k] - hbo;
+                if (v < best) { best = v; bid = 4 * N + N * MO + (k - 1) * s.ns + o; }
+            }
+        }
         if (!(best < -C.eps_active)) { s.done = true; return; }   // primal feasible: optimal
-        const int bid = ti[0];
         const double bsg = (bid < 4 * N && ((upper >> bid) & 1u)) ? -1.0 : 1.0;
-        row_normal<N, MO>(bid, bsg, C.gtil, s.rc, s.rs, s.ft, s.ex, s.ey, s.np);
+        row_normal<N, MO>(bid, bsg, C.gtil, s.rc, s.rs, s.ft, s.ex, s.ey, s.ces, s.ns, s.np);
         double nn = 0.0;
 #pragma unroll
         for (int i = 0; i < NV; ++i) nn += s.np[i] * s.np[i];
@@ -432,12 +457,12 @@ LDCBF_HD void qp_finish(const StepConst& C, const QpState<N, MO>& s, QpSolution<
 // One scenario from start to end (one thread).
 template <int N, int MO, int WS>
 LDCBF_HD void solve_scenario(const StepConst& C, double p0x, double v0x, double p0y, double v0y, double th0, double gx,
-                             double gy, const int (&ft)[N + 1], const double4 (&ce)[MO], int nb, double delta,
-                             double alpha_over_pi, double vmax0, double omega_max, double omega_min, double* ws,
-                             QpSolution<N>& S) {
+                             double gy, const int (&ft)[N + 1], const double4 (&ce)[MO], int nb, const double4* ce_stream,
+                             int n_stream, double delta, double alpha_over_pi, double vmax0, double omega_max,
+                             double omega_min, double* ws, QpSolution<N>& S) {
     QpState<N, MO> s;
-    qp_setup<N, MO, WS>(C, p0x, v0x, p0y, v0y, th0, gx, gy, ft, ce, nb, delta, alpha_over_pi, vmax0, omega_max,
-                        omega_min, ws, s);
+    qp_setup<N, MO, WS>(C, p0x, v0x, p0y, v0y, th0, gx, gy, ft, ce, nb, ce_stream, n_stream, delta, alpha_over_pi, vmax0,
+                        omega_max, omega_min, ws, s);
     while (!s.done) qp_trip<N, MO, WS>(C, ws, s);
     qp_finish<N, MO>(C, s, S);
 }

@@ -66,13 +66,14 @@ __global__ void __launch_bounds__(BLOCK) mpc_qp_kernel(StepConst C, int B, int m
     for (int k = 0; k <= N; ++k) ft[k] = io.foot[(size_t)b * (N + 1) + k];
     double aop, vmax0, omax, omin;
     load_limits(C, io.limits, b, aop, vmax0, omax, omin);
-    const int nb = min(io.nobs[b], MO);
+    const int nt = min(io.nobs[b], max_obs);
+    const int nb = min(nt, MO);
     double4 ce[MO];
     const double4* gce = reinterpret_cast<const double4*>(io.c_eta) + (size_t)b * max_obs;
 #pragma unroll
     for (int o = 0; o < MO; ++o) ce[o] = (o < nb) ? gce[o] : make_double4(0.0, 0.0, 0.0, 0.0);
     QpSolution<N> S;
-    solve_scenario<N, MO, BLOCK>(C, x.x, x.y, x.z, x.w, io.theta0[b], g.x, g.y, ft, ce, nb,
+    solve_scenario<N, MO, BLOCK>(C, x.x, x.y, x.z, x.w, io.theta0[b], g.x, g.y, ft, ce, nb, gce + MO, nt - nb,
                                  io.delta ? io.delta[b] : 0.0, aop, vmax0, omax, omin, qp_ws + threadIdx.x, S);
     store_solution<N>(S, b, io.U, io.X, io.theta, io.omega, io.obj, io.status, io.iters);
 }
@@ -122,12 +123,13 @@ __global__ void __launch_bounds__(BLOCK) mpc_qp_refill_kernel(StepConst C, int B
                     for (int k = 0; k <= N; ++k) ft[k] = io.foot[(size_t)b * (N + 1) + k];
                     double aop, vmax0, omax, omin;
                     load_limits(C, io.limits, b, aop, vmax0, omax, omin);
-                    const int nb = min(io.nobs[b], MO);
+                    const int nt = min(io.nobs[b], max_obs);
+                    const int nb = min(nt, MO);
                     double4 ce[MO];
                     const double4* gce = reinterpret_cast<const double4*>(io.c_eta) + (size_t)b * max_obs;
 #pragma unroll
                     for (int o = 0; o < MO; ++o) ce[o] = (o < nb) ? gce[o] : make_double4(0.0, 0.0, 0.0, 0.0);
-                    qp_setup<N, MO, BLOCK>(C, x.x, x.y, x.z, x.w, io.theta0[b], g.x, g.y, ft, ce, nb,
+                    qp_setup<N, MO, BLOCK>(C, x.x, x.y, x.z, x.w, io.theta0[b], g.x, g.y, ft, ce, nb, gce + MO, nt - nb,
                                            io.delta ? io.delta[b] : 0.0, aop, vmax0, omax, omin, ws, s);
                 }
                 next = min(end, next + __popc(free_m));
@@ -178,8 +180,8 @@ static int launch_qp(const StepConst& C, int B, int max_obs, const StepIO& io, c
 template <int N>
 static int dispatch_obs(const StepConst& C, int B, int max_obs, const StepIO& io, cudaStream_t st) {
     if (max_obs <= 4) return launch_qp<N, 4>(C, B, max_obs, io, st);
-    if (max_obs <= LDCBF_MAX_OBSTACLES) return launch_qp<N, 8>(C, B, max_obs, io, st);
-    return LDCBF_E_SHAPE;
+    // up to 8 obstacles per scenario live in registers; any further ones are streamed from c_eta during the scan
+    return launch_qp<N, 8>(C, B, max_obs, io, st);
 }
 
 }  // namespace ldcbf

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
 #pragma unroll
             for (int k = 0; k <= N; ++k) ft[k] = (((step_number + k) & 1) == (right_first ? 0 : 1)) ? 1 : -1;
             QpSolution<N> S;
-            solve_scenario<N, MO, BLOCK>(C, px, vx, py, vy, th, gx, gy, ft, ce, nb, dl, aop, vmax0, omax, omin,
+            solve_scenario<N, MO, BLOCK>(C, px, vx, py, vy, th, gx, gy, ft, ce, nb, nullptr, 0, dl, aop, vmax0, omax, omin,
                                          qp_ws + threadIdx.x, S);
             ++solves;
             last_status = S.status;

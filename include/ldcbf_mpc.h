@@ -41,7 +41,8 @@ extern "C" {
 #define LDCBF_STATUS_DEGENERATE 3   /* CoM exactly on an obstacle edge: ||x-c|| = 0 (ObstaclesUtils.py:104) */
 #define LDCBF_STATUS_DONE 4         /* rollout only: scenario already stopped (objective < stop_objective) */
 
-/* supported shapes of the register-resident solver */
+/* supported shapes: horizon 1..4 (register-resident solver); any number of obstacles per scenario in
+ * ldcbf_mpc_qp_f64 / ldcbf_mpc_step_f64 (the first 8 in registers, the rest streamed), at most 8 in ldcbf_rollout_f64 */
 #define LDCBF_MAX_HORIZON 4
 #define LDCBF_MAX_OBSTACLES 8
 

@@ -133,3 +133,18 @@ def test_subgoal_sequencing_matches_oracle():
         if end == 0:
             assert ((Xg[[0, 2], -1] - np.array(sg)) ** 2).sum() < 0.2
         s0 = e + 1
+
+
+def test_known_crowded_map_runs_stepwise_with_twenty_obstacles():
+    """The reference's CROWDED map (20 obstacles) as a known map: more obstacles than the rollout kernel holds, so the
+    mirror class runs its stepwise loop (one K1 + one K2+K3 launch per step)."""
+    from HumanoidNavigation.MPC.HumanoidMPCVariants.HumanoidMPCCustomLCBF import HumanoidMPCCustomLCBF
+    from scipy.spatial import ConvexHull
+    geo = helpers.load_geo()
+    hulls = [ConvexHull(p) for p in helpers.map_points(geo, "crowded10")]
+    rings = [h.points[h.vertices] for h in hulls]
+    m = HumanoidMPCCustomLCBF(N_horizon=3, N_mpc_timesteps=80, sampling_time=0.4, goal=(4, 3.5), init_state=(0, 0, 0, 0, np.pi / 2),
+                              obstacles=hulls, verbosity=0, distance_from_obstacles=1e-6)
+    X, U, _ = m.run_simulation(None, make_fast_plot=False, fill_animator=False)
+    assert U.shape[1] >= 10
+    check_run(X, U, (4, 3.5), rings, 0.4, delta=1e-6, N_simul=80)

@@ -194,6 +194,22 @@ def test_many_obstacles_and_per_scenario_limits(L):
     assert n_ok > 40
 
 
+def test_twenty_obstacle_known_map(L):
+    """CROWDED map as a known map (20 obstacles): 8 in registers, 12 streamed from c_eta."""
+    geo = helpers.load_geo()
+    rings = helpers.map_rings(geo, "crowded10")
+    rs = np.random.default_rng(8)
+    B = 128
+    pos = rs.uniform((-0.8, -0.8), (5.0, 4.5), (B, 2))
+    states = np.column_stack((pos[:, 0], rs.uniform(-0.2, 0.2, B), pos[:, 1], rs.uniform(-0.2, 0.2, B), rs.uniform(-2, 2, B)))
+    goals = np.tile([4.0, 3.5], (B, 1))
+    foots = np.tile([1, -1, 1, -1], (B, 1)).astype(np.int8)
+    deltas = np.where(np.arange(B) % 2 == 0, 0.0, 0.05)
+    out, nobs = _run_steps(L, states, goals, foots, [rings] * B, deltas)
+    ref = helpers.oracle_steps(states, goals, foots, [rings] * B, deltas)
+    assert _compare(out, ref, nobs, foots, deltas) > 60
+
+
 def test_infeasible_and_degenerate_status(L):
     geo = helpers.load_geo()
     rings = helpers.map_rings(geo, "circles")

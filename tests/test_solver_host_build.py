@@ -106,3 +106,21 @@ def test_host_build_on_config2_batch(host_lib):
     d = np.array([np.abs(out["U"][b] - r["U"]).max() for b, r in enumerate(ref) if r["status"] == 0])
     assert np.percentile(d, 99) < 1e-9
     assert out["iters"].max() <= 60
+
+
+def test_host_build_with_streamed_obstacles(host_lib):
+    """More than the register-resident obstacles: the CROWDED map (20 obstacles, `Scenario.py:54-69`) as a KNOWN map."""
+    geo = helpers.load_geo()
+    rings = helpers.map_rings(geo, "crowded10")
+    rs = np.random.default_rng(4)
+    B = 96
+    pos = rs.uniform((-0.8, -0.8), (5.0, 4.5), (B, 2))
+    states = np.column_stack((pos[:, 0], rs.uniform(-0.2, 0.2, B), pos[:, 1], rs.uniform(-0.2, 0.2, B), rs.uniform(-2, 2, B)))
+    goals = np.tile([4.0, 3.5], (B, 1))
+    foots = np.tile([1, -1, 1, -1], (B, 1)).astype(np.int8)
+    ce, nobs = c_eta_of(states, [rings] * B)
+    assert ce.shape[1] == 20
+    out = host_solve(host_lib, states, goals, foots, ce, nobs, np.zeros(B))
+    ref = helpers.oracle_steps(states, goals, foots, [rings] * B, np.zeros(B))
+    assert compare(out, ref) < 1e-6
+    assert sum(r["status"] == 0 for r in ref) > 50
