@@ -260,7 +260,7 @@ def run_ours(args):
         line["e2e"] = {"value": B * args.steps * world / (e2e_ms * 1e-3), "unit": UNIT,
                        "h2d_bytes_per_step": e2e_res["h2d"], "d2h_bytes_per_step": e2e_res["d2h"],
                        "ms_per_step": e2e_ms / args.steps,
-                       "api": "BatchedHumanoidMPC.step_host (pinned host state in, next state / u0 / obj / status out)"}
+                       "api": "BatchedHumanoidMPC.step_host -> ldcbf_mpc_step_packed_f64 (pinned host state/foot in, next rows / obj / status out)"}
         if rank == 0:
             # ---- kernel-only timing of the dominant kernel for the roofline (same inputs, L2 flushed)
             t_qp = timed_steps(lambda: L.mpc_qp(prm, d["x0"], d["th"], d["goal"], d["foot"], out["c_eta"], d["nobs"],

@@ -20,24 +20,43 @@ struct StepIO {
     const double* x0; const double* theta0; const double* goal; const int8_t* foot;
     const double* c_eta; const int32_t* nobs; const double* delta; const double* limits;
     double* U; double* X; double* theta; double* omega; double* obj; int32_t* status; int32_t* iters;
+    // loop-shaped variant (ldcbf_mpc_step_packed_f64): state rows [B,5] in (x0/theta0 unused), next rows [B,8] out
+    const double* state5; double* next8;
 };
 
+__device__ __forceinline__ void load_state(const StepIO& io, int b, double4& x, double& th) {
+    if (io.state5) {
+        const double* s = io.state5 + 5 * (size_t)b;
+        x = make_double4(s[0], s[1], s[2], s[3]);
+        th = s[4];
+    } else {
+        x = reinterpret_cast<const double4*>(io.x0)[b];          // (p_x, v_x, p_y, v_y)
+        th = io.theta0[b];
+    }
+}
+
 template <int N>
-__device__ __forceinline__ void store_solution(const QpSolution<N>& S, int b, double* U, double* X, double* theta,
-                                               double* omega, double* obj, int32_t* status, int32_t* iters) {
-    double2* U2 = reinterpret_cast<double2*>(U) + (size_t)b * N;
-    double4* X4 = reinterpret_cast<double4*>(X) + (size_t)b * (N + 1);
+__device__ __forceinline__ void store_solution(const QpSolution<N>& S, int b, const StepIO& io) {
+    if (io.next8) {     // (x_next[4], theta_1, u0_x, u0_y, omega_0)
+        double4* o = reinterpret_cast<double4*>(io.next8) + 2 * (size_t)b;
+        o[0] = make_double4(S.px[1], S.vx[1], S.py[1], S.vy[1]);
+        o[1] = make_double4(S.th[1], S.ux[0], S.uy[0], S.om[0]);
+    }
+    if (io.U) {
+        double2* U2 = reinterpret_cast<double2*>(io.U) + (size_t)b * N;
+        double4* X4 = reinterpret_cast<double4*>(io.X) + (size_t)b * (N + 1);
 #pragma unroll
-    for (int k = 0; k < N; ++k) U2[k] = make_double2(S.ux[k], S.uy[k]);
+        for (int k = 0; k < N; ++k) U2[k] = make_double2(S.ux[k], S.uy[k]);
 #pragma unroll
-    for (int k = 0; k <= N; ++k) X4[k] = make_double4(S.px[k], S.vx[k], S.py[k], S.vy[k]);
+        for (int k = 0; k <= N; ++k) X4[k] = make_double4(S.px[k], S.vx[k], S.py[k], S.vy[k]);
 #pragma unroll
-    for (int k = 0; k <= N; ++k) theta[(size_t)b * (N + 1) + k] = S.th[k];
+        for (int k = 0; k <= N; ++k) io.theta[(size_t)b * (N + 1) + k] = S.th[k];
 #pragma unroll
-    for (int k = 0; k < N; ++k) omega[(size_t)b * N + k] = S.om[k];
-    obj[b] = S.obj;
-    status[b] = S.status;
-    iters[b] = S.iters;
+        for (int k = 0; k < N; ++k) io.omega[(size_t)b * N + k] = S.om[k];
+    }
+    io.obj[b] = S.obj;
+    io.status[b] = S.status;
+    io.iters[b] = S.iters;
 }
 
 __device__ __forceinline__ void load_limits(const StepConst& C, const double* limits, int b, double& aop,
@@ -59,7 +78,9 @@ __global__ void __launch_bounds__(BLOCK) mpc_qp_kernel(StepConst C, int B, int m
     extern __shared__ double qp_ws[];
     const int b = blockIdx.x * BLOCK + threadIdx.x;
     if (b >= B) return;
-    const double4 x = reinterpret_cast<const double4*>(io.x0)[b];          // (p_x, v_x, p_y, v_y)
+    double4 x;
+    double th0;
+    load_state(io, b, x, th0);
     const double2 g = reinterpret_cast<const double2*>(io.goal)[b];
     int ft[N + 1];
 #pragma unroll
@@ -73,9 +94,9 @@ __global__ void __launch_bounds__(BLOCK) mpc_qp_kernel(StepConst C, int B, int m
 #pragma unroll
     for (int o = 0; o < MO; ++o) ce[o] = (o < nb) ? gce[o] : make_double4(0.0, 0.0, 0.0, 0.0);
     QpSolution<N> S;
-    solve_scenario<N, MO, BLOCK>(C, x.x, x.y, x.z, x.w, io.theta0[b], g.x, g.y, ft, ce, nb, gce + MO, nt - nb,
+    solve_scenario<N, MO, BLOCK>(C, x.x, x.y, x.z, x.w, th0, g.x, g.y, ft, ce, nb, gce + MO, nt - nb,
                                  io.delta ? io.delta[b] : 0.0, aop, vmax0, omax, omin, qp_ws + threadIdx.x, S);
-    store_solution<N>(S, b, io.U, io.X, io.theta, io.omega, io.obj, io.status, io.iters);
+    store_solution<N>(S, b, io);
 }
 
 // Large-batch variant: persistent warps with lane refill.  A warp of the plain kernel runs until its slowest lane
@@ -108,7 +129,7 @@ __global__ void __launch_bounds__(BLOCK) mpc_qp_refill_kernel(StepConst C, int B
             if (b >= 0 && s.done) {
                 QpSolution<N> S;
                 qp_finish<N, MO>(C, s, S);
-                store_solution<N>(S, b, io.U, io.X, io.theta, io.omega, io.obj, io.status, io.iters);
+                store_solution<N>(S, b, io);
                 b = -1;
             }
             if (more) {
@@ -116,7 +137,9 @@ __global__ void __launch_bounds__(BLOCK) mpc_qp_refill_kernel(StepConst C, int B
                 const int cand = next + __popc(free_m & ((1u << lane) - 1u));
                 if (b < 0 && cand < end) {
                     b = cand;
-                    const double4 x = reinterpret_cast<const double4*>(io.x0)[b];
+                    double4 x;
+                    double th0;
+                    load_state(io, b, x, th0);
                     const double2 g = reinterpret_cast<const double2*>(io.goal)[b];
                     int ft[N + 1];
 #pragma unroll
@@ -129,7 +152,7 @@ __global__ void __launch_bounds__(BLOCK) mpc_qp_refill_kernel(StepConst C, int B
                     const double4* gce = reinterpret_cast<const double4*>(io.c_eta) + (size_t)b * max_obs;
 #pragma unroll
                     for (int o = 0; o < MO; ++o) ce[o] = (o < nb) ? gce[o] : make_double4(0.0, 0.0, 0.0, 0.0);
-                    qp_setup<N, MO, BLOCK>(C, x.x, x.y, x.z, x.w, io.theta0[b], g.x, g.y, ft, ce, nb, gce + MO, nt - nb,
+                    qp_setup<N, MO, BLOCK>(C, x.x, x.y, x.z, x.w, th0, g.x, g.y, ft, ce, nb, gce + MO, nt - nb,
                                            io.delta ? io.delta[b] : 0.0, aop, vmax0, omax, omin, ws, s);
                 }
                 next = min(end, next + __popc(free_m));
@@ -184,6 +207,18 @@ static int dispatch_obs(const StepConst& C, int B, int max_obs, const StepIO& io
     return launch_qp<N, 8>(C, B, max_obs, io, st);
 }
 
+static int dispatch_horizon(const ldcbf_params& prm, int B, int N, int max_obs, const StepIO& io, void* cuda_stream) {
+    const StepConst C = make_const(prm);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    switch (N) {
+        case 1: return dispatch_obs<1>(C, B, max_obs, io, st);
+        case 2: return dispatch_obs<2>(C, B, max_obs, io, st);
+        case 3: return dispatch_obs<3>(C, B, max_obs, io, st);
+        case 4: return dispatch_obs<4>(C, B, max_obs, io, st);
+        default: return LDCBF_E_SHAPE;
+    }
+}
+
 }  // namespace ldcbf
 
 using namespace ldcbf;
@@ -215,16 +250,26 @@ extern "C" int ldcbf_mpc_qp_f64(const ldcbf_params* prm, int B, int N, int max_o
     if (B == 0) return LDCBF_OK;
     if (!x0 || !theta0 || !goal || !foot || !c_eta || !nobs || !U || !X || !theta || !omega || !obj || !status || !iters)
         return LDCBF_E_ARG;
-    const StepConst C = make_const(*prm);
-    const StepIO io{x0, theta0, goal, foot, c_eta, nobs, delta, limits, U, X, theta, omega, obj, status, iters};
-    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    switch (N) {
-        case 1: return dispatch_obs<1>(C, B, max_obs, io, st);
-        case 2: return dispatch_obs<2>(C, B, max_obs, io, st);
-        case 3: return dispatch_obs<3>(C, B, max_obs, io, st);
-        case 4: return dispatch_obs<4>(C, B, max_obs, io, st);
-        default: return LDCBF_E_SHAPE;
-    }
+    const StepIO io{x0, theta0, goal, foot, c_eta, nobs, delta, limits, U, X, theta, omega, obj, status, iters,
+                    nullptr, nullptr};
+    return dispatch_horizon(*prm, B, N, max_obs, io, cuda_stream);
+}
+
+extern "C" int ldcbf_mpc_step_packed_f64(const ldcbf_params* prm, int B, int N, int max_obs, int max_verts,
+                                         const double* state, const double* goal, const int8_t* foot,
+                                         const double* verts, const int32_t* nverts, const int32_t* nobs,
+                                         const double* delta, const double* limits, double* next, double* c_eta,
+                                         double* obj, int32_t* status, int32_t* iters, void* cuda_stream) {
+    if (!prm || B < 0 || max_obs <= 0 || max_verts <= 0) return LDCBF_E_ARG;
+    if (B == 0) return LDCBF_OK;
+    if (!state || !goal || !foot || !verts || !nverts || !nobs || !next || !c_eta || !obj || !status || !iters)
+        return LDCBF_E_ARG;
+    int rc = launch_halfplanes(B, max_obs, max_verts, state, 5, 2, verts, nverts, nobs, c_eta,
+                               (prm->flags & LDCBF_FLAG_FAST_GEOMETRY) != 0, cuda_stream);
+    if (rc != LDCBF_OK) return rc;
+    const StepIO io{nullptr, nullptr, goal, foot, c_eta, nobs, delta, limits, nullptr, nullptr, nullptr, nullptr,
+                    obj, status, iters, state, next};
+    return dispatch_horizon(*prm, B, N, max_obs, io, cuda_stream);
 }
 
 extern "C" int ldcbf_mpc_step_f64(const ldcbf_params* prm, int B, int N, int max_obs, int max_verts, const double* x0,

@@ -52,29 +52,23 @@ class BatchedHumanoidMPC:
     # ---- end-to-end step: host buffers in, host buffers out -----------------------------------------------
     def step_host(self, state_host, foot_host):
         """state_host: pinned [B,5] fp64 tensor (p_x, v_x, p_y, v_y, theta); foot_host: pinned [B,N+1] int8.
-        Copies the inputs host->device, runs the step, copies (U[:,0], X[:,1], theta[:,1], omega[:,0], obj,
-        status) back into pinned host buffers and synchronises.  Returns the dict of pinned host tensors."""
+        Copies the inputs host->device, runs the loop-shaped step (`ldcbf_mpc_step_packed_f64`), copies
+        next[B,8] = (x_next[4], theta_1, u0_x, u0_y, omega_0), obj and status back into pinned host buffers and
+        synchronises.  Returns the dict of pinned host tensors (reused between calls)."""
         B, N = self.B, self.N
         if self._pinned is None:
             pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
-            self._pinned = dict(next_state=pin((B, 5), torch.float64), u0=pin((B, 3), torch.float64),
-                                obj=pin((B,), torch.float64), status=pin((B,), torch.int32))
+            self._pinned = dict(next=pin((B, 8), torch.float64), obj=pin((B,), torch.float64),
+                                status=pin((B,), torch.int32))
             self._d_state = torch.empty((B, 5), dtype=torch.float64, device=self.device)
             self._d_foot = torch.empty((B, N + 1), dtype=torch.int8, device=self.device)
-            self._d_next = torch.empty((B, 5), dtype=torch.float64, device=self.device)
-            self._d_u0 = torch.empty((B, 3), dtype=torch.float64, device=self.device)
+            self._packed = None
         self._d_state.copy_(state_host, non_blocking=True)
         self._d_foot.copy_(foot_host, non_blocking=True)
-        x0 = self._d_state[:, :4].contiguous()
-        th0 = self._d_state[:, 4].contiguous()
-        o = self.step(x0, th0, self._d_foot)
-        self._d_next[:, :4] = o["X"][:, 1]
-        self._d_next[:, 4] = o["theta"][:, 1]
-        self._d_u0[:, :2] = o["U"][:, 0]
-        self._d_u0[:, 2] = o["omega"][:, 0]
+        o = self._packed = _b.mpc_step_packed(self.prm, self._d_state, self.goal, self._d_foot, self.verts, self.nverts,
+                                              self.nobs, delta=self.delta, limits=self.limits, out=self._packed)
         p = self._pinned
-        p["next_state"].copy_(self._d_next, non_blocking=True)
-        p["u0"].copy_(self._d_u0, non_blocking=True)
+        p["next"].copy_(o["next"], non_blocking=True)
         p["obj"].copy_(o["obj"], non_blocking=True)
         p["status"].copy_(o["status"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -86,7 +80,7 @@ class BatchedHumanoidMPC:
 
     @property
     def d2h_bytes_per_step(self):
-        return self.B * (5 * 8 + 3 * 8 + 8 + 4)
+        return self.B * (8 * 8 + 8 + 4)
 
     # ---- closed loop -----------------------------------------------------------------------------------------
     def rollout(self, state, right_first, T, goals=None, max_steps_per_goal=None, record=True):

@@ -12,7 +12,8 @@ LIB_PATH = os.environ.get("LDCBF_B200_LIB") or os.path.join(_HERE, "libldcbf_b20
 MAX_OBSTACLES = 8      # LDCBF_MAX_OBSTACLES of include/ldcbf_mpc.h
 
 EXPORTS = ("ldcbf_abi_version", "ldcbf_params_default", "ldcbf_last_cuda_error", "ldcbf_workspace_bytes",
-           "ldcbf_halfplanes_f64", "ldcbf_mpc_qp_f64", "ldcbf_mpc_step_f64", "ldcbf_lidar_cast_f64",
+           "ldcbf_halfplanes_f64", "ldcbf_mpc_qp_f64", "ldcbf_mpc_step_f64", "ldcbf_mpc_step_packed_f64",
+           "ldcbf_lidar_cast_f64",
            "ldcbf_lidar_clusters_f64",
            "ldcbf_rollout_f64", "ldcbf_probe_fp64_fma")
 
@@ -54,6 +55,7 @@ def lib():
         L.ldcbf_halfplanes_f64.argtypes = [c_int, c_int, c_int, P, P, P, P, P, P]
         L.ldcbf_mpc_qp_f64.argtypes = [POINTER(LdcbfParams), c_int, c_int, c_int] + [P] * 16
         L.ldcbf_mpc_step_f64.argtypes = [POINTER(LdcbfParams), c_int, c_int, c_int, c_int] + [P] * 19
+        L.ldcbf_mpc_step_packed_f64.argtypes = [POINTER(LdcbfParams), c_int, c_int, c_int, c_int] + [P] * 14
         L.ldcbf_lidar_cast_f64.argtypes = [c_int, c_int, P, c_double, P, c_int, c_int, P, P, P, P, P, P, P]
         L.ldcbf_lidar_clusters_f64.argtypes = [c_int, c_int, P, P, c_double, c_int, c_int, c_int, P, P, P, P, P, P]
         L.ldcbf_rollout_f64.argtypes = [POINTER(LdcbfParams)] + [c_int] * 7 + [P] * 15
@@ -173,6 +175,27 @@ def mpc_step(prm, x0, theta0, goal, foot, verts, nverts, nobs, delta=None, warm=
                                     _ptr(out["c_eta"], F64, "c_eta"), _ptr(out["obj"], F64, "obj"),
                                     _ptr(out["status"], I32, "status"), _ptr(out["iters"], I32, "iters"), _stream()),
            "ldcbf_mpc_step_f64")
+    return out
+
+
+def mpc_step_packed(prm, state, goal, foot, verts, nverts, nobs, delta=None, limits=None, out=None):
+    """Loop-shaped step: state[B,5] in -> dict(next[B,8] = (x_next[4], theta_1, u0_x, u0_y, omega_0), c_eta, obj,
+    status, iters)."""
+    B, N = state.shape[0], foot.shape[1] - 1
+    max_obs, max_verts = verts.shape[1], verts.shape[2]
+    out = {} if out is None else out
+    dev = state.device
+    for name, shape, dt in (("next", (B, 8), F64), ("c_eta", (B, max_obs, 4), F64), ("obj", (B,), F64),
+                            ("status", (B,), I32), ("iters", (B,), I32)):
+        if out.get(name) is None:
+            out[name] = torch.empty(shape, dtype=dt, device=dev)
+    _check(lib().ldcbf_mpc_step_packed_f64(ctypes.byref(prm), B, N, max_obs, max_verts, _ptr(state, F64, "state"),
+                                           _ptr(goal, F64, "goal"), _ptr(foot, I8, "foot"), _ptr(verts, F64, "verts"),
+                                           _ptr(nverts, I32, "nverts"), _ptr(nobs, I32, "nobs"),
+                                           _ptr(delta, F64, "delta"), _ptr(limits, F64, "limits"),
+                                           _ptr(out["next"], F64, "next"), _ptr(out["c_eta"], F64, "c_eta"),
+                                           _ptr(out["obj"], F64, "obj"), _ptr(out["status"], I32, "status"),
+                                           _ptr(out["iters"], I32, "iters"), _stream()), "ldcbf_mpc_step_packed_f64")
     return out
 
 

@@ -210,6 +210,27 @@ def test_twenty_obstacle_known_map(L):
     assert _compare(out, ref, nobs, foots, deltas) > 60
 
 
+def test_packed_step_and_host_path_equal_the_plain_step(L):
+    """ldcbf_mpc_step_packed_f64 (state rows in, next rows out) and BatchedHumanoidMPC.step_host give the same numbers."""
+    from ldcbf_b200 import scenarios
+    sc = scenarios.config2(300, seed=13)
+    foots = scenarios.foot_window(sc["right_first"], 0, 3)
+    verts, nverts, nobs = cu(sc["verts"]), cu(sc["nverts"], torch.int32), cu(sc["nobs"], torch.int32)
+    prm = L.default_params(0.4)
+    a = L.mpc_step(prm, cu(sc["state"][:, :4]), cu(sc["state"][:, 4]), cu(sc["goal"]), cu(foots, torch.int8), verts, nverts, nobs)
+    b = L.mpc_step_packed(prm, cu(sc["state"]), cu(sc["goal"]), cu(foots, torch.int8), verts, nverts, nobs)
+    nxt = b["next"].cpu().numpy()
+    ok = a["status"].cpu().numpy() == 0
+    assert np.array_equal(a["status"].cpu().numpy(), b["status"].cpu().numpy())
+    assert np.array_equal(nxt[ok, :4], a["X"][:, 1].cpu().numpy()[ok])
+    assert np.array_equal(nxt[ok, 4], a["theta"][:, 1].cpu().numpy()[ok])
+    assert np.array_equal(nxt[ok, 5:7], a["U"][:, 0].cpu().numpy()[ok])
+    assert np.array_equal(nxt[ok, 7], a["omega"][:, 0].cpu().numpy()[ok])
+    eng = L.BatchedHumanoidMPC(sc["goal"], sc["verts"], sc["nverts"], sc["nobs"], N_horizon=3, sampling_time=0.4)
+    h = eng.step_host(torch.as_tensor(sc["state"]).pin_memory(), torch.as_tensor(foots).pin_memory())
+    assert np.array_equal(h["next"].numpy()[ok], nxt[ok]) and np.array_equal(h["status"].numpy(), b["status"].cpu().numpy())
+
+
 def test_infeasible_and_degenerate_status(L):
     geo = helpers.load_geo()
     rings = helpers.map_rings(geo, "circles")
