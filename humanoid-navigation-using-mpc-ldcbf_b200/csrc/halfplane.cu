@@ -56,6 +56,49 @@ __global__ void __launch_bounds__(K1_THREADS) halfplane_kernel(int n_pairs, int 
     c_eta[pair] = halfplane_serial<EXACT>(px, py, srings + threadIdx.x * sstride, V);
 }
 
+// Small-batch variant: G lanes per (scenario, obstacle) pair, lane l takes edges l, l+G, ...  With a few thousand
+// scenarios the thread-per-ring kernel above leaves most of the GPU idle and its latency is one serial walk over
+// the ring (15 us at B = 4096); splitting each ring over 8 lanes cuts that walk to 3 edges.  Same per-edge
+// arithmetic; the first strict minimum is kept by an xor-butterfly that breaks ties towards the lower edge index,
+// the crossing parity is summed.
+template <bool EXACT, int G>
+__global__ void __launch_bounds__(128) halfplane_split_kernel(int n_pairs, int max_obs, int max_verts,
+                                                              const double* __restrict__ pos, int pos_stride, int y_off,
+                                                              const double2* __restrict__ verts,
+                                                              const int32_t* __restrict__ nverts,
+                                                              const int32_t* __restrict__ nobs,
+                                                              double4* __restrict__ c_eta) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int pair = tid / G, lane = tid % G;
+    if (pair >= n_pairs) return;                    // whole groups leave together (blockDim is a multiple of G)
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+    const int b = pair / max_obs, o = pair - b * max_obs;
+    const int V = (o < nobs[b]) ? min(nverts[pair], max_verts) : 0;
+    if (V <= 0) {
+        if (lane == 0) c_eta[pair] = make_double4(0.0, 0.0, 0.0, 0.0);
+        return;
+    }
+    const double px = pos[(size_t)b * pos_stride], py = pos[(size_t)b * pos_stride + y_off];
+    const double2* ring = verts + (size_t)pair * max_verts;
+    double best = INFINITY, bcx = 0.0, bcy = 0.0;
+    int be = 0x7fffffff, cross = 0;
+    for (int e = lane; e < V; e += G) {
+        const double2 A = __ldg(ring + e), Bv = __ldg(ring + ((e + 1 == V) ? 0 : e + 1));
+        double cx, cy;
+        const double key = edge_closest<EXACT>(px, py, A, Bv, cx, cy, cross);
+        if (key < best) { best = key; bcx = cx; bcy = cy; be = e; }
+    }
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) {
+        const double ok = __shfl_xor_sync(gmask, best, off, G);
+        const double ocx = __shfl_xor_sync(gmask, bcx, off, G), ocy = __shfl_xor_sync(gmask, bcy, off, G);
+        const int oe = __shfl_xor_sync(gmask, be, off, G);
+        cross += __shfl_xor_sync(gmask, cross, off, G);
+        if (ok < best || (ok == best && oe < be)) { best = ok; bcx = ocx; bcy = ocy; be = oe; }
+    }
+    if (lane == 0) c_eta[pair] = finish_halfplane<EXACT>(px, py, bcx, bcy, cross);
+}
+
 int launch_halfplanes(int B, int max_obs, int max_verts, const double* pos, int pos_stride, int y_off,
                       const double* verts, const int32_t* nverts, const int32_t* nobs, double* c_eta,
                       bool fast_geometry, void* cuda_stream) {
@@ -64,6 +107,16 @@ int launch_halfplanes(int B, int max_obs, int max_verts, const double* pos, int 
     if (!pos || !verts || !nverts || !nobs || !c_eta) return LDCBF_E_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     const int n_pairs = B * max_obs;
+    if ((long long)n_pairs * 8 <= 148 * 2048 && max_verts > 8) {       // the GPU has idle lanes: split every ring over 8
+        const unsigned grid = (unsigned)(((size_t)n_pairs * 8 + 127) / 128);
+        const double2* v2 = reinterpret_cast<const double2*>(verts);
+        double4* ce = reinterpret_cast<double4*>(c_eta);
+        if (fast_geometry)
+            halfplane_split_kernel<false, 8><<<grid, 128, 0, st>>>(n_pairs, max_obs, max_verts, pos, pos_stride, y_off, v2, nverts, nobs, ce);
+        else
+            halfplane_split_kernel<true, 8><<<grid, 128, 0, st>>>(n_pairs, max_obs, max_verts, pos, pos_stride, y_off, v2, nverts, nobs, ce);
+        return check_launch();
+    }
     const int sstride = max_verts | 1;                                  // odd stride in 16-byte units
     const size_t smem = (size_t)K1_THREADS * sstride * sizeof(double2);
     if (smem > 200 * 1024) return LDCBF_E_SHAPE;
