@@ -9,40 +9,63 @@
 //                                                            dropped again by the ConvexHull call of
 //                                                            HumanoidMPCUnknownEnvironment.py:55, so it is not emitted)
 //
-// One CTA per scan (R <= 512 rays).  DBSCAN on <= 512 points is done exactly as sklearn defines it:
+// One 128-thread CTA per scan (R <= 512 rays).  DBSCAN on <= 512 points is done exactly as sklearn defines it:
 //   * neighbourhood = points within eps (squared distances, self included); core = at least min_samples neighbours;
 //   * clusters = connected components of core points, numbered by their smallest core-point index (sklearn visits
 //     points in index order and opens a cluster at the first unvisited core point);
 //   * a border point takes the lowest-numbered cluster among its core neighbours (it is labelled by the first
 //     cluster that reaches it and never relabelled); everything else is noise (-1).
 // The eps-graph is held as a bit matrix in shared memory (R x R/32 words), components by min-label propagation.
-// Hulls: lexicographic bitonic sort of the cluster (np.unique order), duplicate removal, collinearity test, Andrew's
-// monotone chain (counter-clockwise, strictly convex).  Qhull and the chain may disagree on which of several
-// points that are collinear to 1e-16 is called a vertex; the polygons are the same to rounding.
+// Hulls: ONE bitonic sort of all clustered points by (cluster, x, y) turns every cluster into a contiguous segment in
+// np.unique order; then one thread per cluster removes duplicates, tests flatness and runs Andrew's monotone chain
+// (counter-clockwise, strictly convex), all clusters concurrently.  Qhull and the chain may disagree on which of
+// several points that are collinear to 1e-16 is called a vertex; the polygons are the same to rounding.
 #include "ldcbf_common.cuh"
 
 namespace ldcbf {
 
 constexpr int CL_RMAX = 512;
-constexpr int CL_WORDS = CL_RMAX / 32;
-constexpr int CL_THREADS = 256;
+constexpr int CL_THREADS = 128;
 constexpr int CL_BIG = 0x3fffffff;
 
-struct ClusterShared {
-    double x[CL_RMAX], y[CL_RMAX];          // compacted valid points, ray order
-    double sx[CL_RMAX], sy[CL_RMAX];        // sort buffer of one cluster
-    unsigned adj[CL_RMAX][CL_WORDS];        // eps-graph
-    unsigned coremask[CL_WORDS];
-    int ray[CL_RMAX];                       // ray index of compacted point i
-    int lab[CL_RMAX];                       // component label = smallest core index, CL_BIG = noise
-    int cid[CL_RMAX];                       // cluster number of root i
-    int hull[CL_RMAX + 2];
-    int P, n_clusters, changed, cnt, hull_n;
-    double red[CL_THREADS / 32][2];
+// Shared-memory layout, sized by RP = R rounded up to 32 (and the sort arrays to the next power of two NS):
+//   double x[RP], y[RP]            compacted valid points, ray order
+//   double sx[NS], sy[NS]          all clustered points sorted by (cluster, x, y)
+//   int    sc[NS]                  cluster number of the sorted points (CL_BIG = noise / padding)
+//   unsigned adj[RP][RP/32]        eps-graph
+//   unsigned coremask[RP/32]
+//   int ray[RP], lab[RP], cid[RP]  ray index; component label (smallest core index); cluster number of a root
+//   int hull[NS + 64]              hull stacks, one region per cluster
+//   int seg0[64], segn[64], hn[64] segment start / length / hull size per cluster (at most 64 clusters are hulled)
+struct ClusterLayout {
+    int RP, W, NS;
+    size_t off_y, off_sx, off_sy, off_sc, off_adj, off_core, off_ray, off_lab, off_cid, off_hull, off_seg, bytes;
+    __host__ __device__ explicit ClusterLayout(int R) {
+        RP = (R + 31) & ~31;
+        W = RP / 32;
+        NS = 32;
+        while (NS < RP) NS <<= 1;
+        size_t o = 0;
+        o += sizeof(double) * RP; off_y = o;
+        o += sizeof(double) * RP; off_sx = o;
+        o += sizeof(double) * NS; off_sy = o;
+        o += sizeof(double) * NS; off_sc = o;
+        o += sizeof(int) * NS; off_adj = o;
+        o += sizeof(unsigned) * RP * W; off_core = o;
+        o += sizeof(unsigned) * W; off_ray = o;
+        o += sizeof(int) * RP; off_lab = o;
+        o += sizeof(int) * RP; off_cid = o;
+        o += sizeof(int) * RP; off_hull = o;
+        o += sizeof(int) * (NS + 64); off_seg = o;
+        o += sizeof(int) * 64 * 3;
+        bytes = (o + 15) & ~(size_t)15;
+    }
 };
 
-__device__ __forceinline__ bool lex_less(double ax, double ay, double bx, double by) {
-    return ax < bx || (ax == bx && ay < by);
+constexpr int CL_MAXC = 64;
+
+__device__ __forceinline__ bool key_less(int ac, double ax, double ay, int bc, double bx, double by) {
+    return ac < bc || (ac == bc && (ax < bx || (ax == bx && ay < by)));
 }
 
 __global__ void __launch_bounds__(CL_THREADS) lidar_clusters_kernel(int R, const double2* __restrict__ hit_xy,
@@ -53,91 +76,106 @@ __global__ void __launch_bounds__(CL_THREADS) lidar_clusters_kernel(int R, const
                                                                     int32_t* __restrict__ hull_nverts,
                                                                     int32_t* __restrict__ n_hulls,
                                                                     int32_t* __restrict__ overflow) {
-    extern __shared__ unsigned char cl_raw[];
-    ClusterShared& S = *reinterpret_cast<ClusterShared*>(cl_raw);
+    extern __shared__ __align__(16) unsigned char cl_raw[];
+    const ClusterLayout Lo(R);
+    const int W = Lo.W;
+    double* X = reinterpret_cast<double*>(cl_raw);
+    double* Y = reinterpret_cast<double*>(cl_raw + Lo.off_y);
+    double* SX = reinterpret_cast<double*>(cl_raw + Lo.off_sx);
+    double* SY = reinterpret_cast<double*>(cl_raw + Lo.off_sy);
+    int* SC = reinterpret_cast<int*>(cl_raw + Lo.off_sc);
+    unsigned* ADJ = reinterpret_cast<unsigned*>(cl_raw + Lo.off_adj);
+    unsigned* CORE = reinterpret_cast<unsigned*>(cl_raw + Lo.off_core);
+    int* RAY = reinterpret_cast<int*>(cl_raw + Lo.off_ray);
+    int* LAB = reinterpret_cast<int*>(cl_raw + Lo.off_lab);
+    int* CID = reinterpret_cast<int*>(cl_raw + Lo.off_cid);
+    int* HULL = reinterpret_cast<int*>(cl_raw + Lo.off_hull);
+    int* SEG0 = reinterpret_cast<int*>(cl_raw + Lo.off_seg);
+    int* SEGN = SEG0 + CL_MAXC;
+    int* HN = SEGN + CL_MAXC;
+    __shared__ int sP, sNC, sChanged;
+
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31;
     const double2* scan = hit_xy + (size_t)b * R;
 
-    // ---- 1. compact the valid readings in ray order (warp 0: ballot + popc per chunk of 32 rays)
+    // ---- 1. load (+ noise) into the sort buffer, then compact the valid readings in ray order (warp 0)
+    for (int i = t; i < R; i += CL_THREADS) {
+        double2 p = scan[i];
+        if (p.x == p.x && noise) { const double2 nz = noise[(size_t)b * R + i]; p.x += nz.x; p.y += nz.y; }
+        SX[i] = p.x; SY[i] = p.y;
+        labels[(size_t)b * R + i] = -1;
+    }
+    if (t < W) CORE[t] = 0u;
+    __syncthreads();
     if (t < 32) {
         int base = 0;
         for (int c = 0; c < R; c += 32) {
             const int i = c + lane;
-            double2 p = make_double2(0.0, 0.0);
-            bool ok = false;
-            if (i < R) {
-                p = scan[i];
-                ok = p.x == p.x;
-                if (ok && noise) { const double2 nz = noise[(size_t)b * R + i]; p.x += nz.x; p.y += nz.y; }
-            }
+            const double px = i < R ? SX[i] : 0.0, py = i < R ? SY[i] : 0.0;
+            const bool ok = i < R && px == px;
             const unsigned m = __ballot_sync(0xffffffffu, ok);
-            if (ok) {
-                const int k = base + __popc(m & ((1u << lane) - 1u));
-                S.x[k] = p.x; S.y[k] = p.y; S.ray[k] = i;
-            }
+            if (ok) { const int k = base + __popc(m & ((1u << lane) - 1u)); X[k] = px; Y[k] = py; RAY[k] = i; }
             base += __popc(m);
         }
-        if (lane == 0) { S.P = base; S.n_clusters = 0; }
+        if (lane == 0) { sP = base; sNC = 0; }
     }
-    for (int i = t; i < R; i += CL_THREADS) labels[(size_t)b * R + i] = -1;
-    if (t < CL_WORDS) S.coremask[t] = 0u;
     __syncthreads();
-    const int P = S.P;
+    const int P = sP;
 
     // ---- 2. eps-graph and core points
     for (int i = t; i < P; i += CL_THREADS) {
-        const double xi = S.x[i], yi = S.y[i];
+        const double xi = X[i], yi = Y[i];
         int count = 0;
         for (int w = 0; w * 32 < P; ++w) {
             unsigned bits = 0u;
             const int jend = min(32, P - w * 32);
             for (int jj = 0; jj < jend; ++jj) {
-                const double dx = S.x[w * 32 + jj] - xi, dy = S.y[w * 32 + jj] - yi;
+                const double dx = X[w * 32 + jj] - xi, dy = Y[w * 32 + jj] - yi;
                 if (dx * dx + dy * dy <= eps2) bits |= 1u << jj;
             }
-            S.adj[i][w] = bits;
+            ADJ[i * W + w] = bits;
             count += __popc(bits);
         }
         const bool core = count >= min_samples;
-        S.lab[i] = core ? i : CL_BIG;
-        if (core) atomicOr(&S.coremask[i >> 5], 1u << (i & 31));
+        LAB[i] = core ? i : CL_BIG;
+        if (core) atomicOr(&CORE[i >> 5], 1u << (i & 31));
     }
     __syncthreads();
 
     // ---- 3. connected components of the core points: min-label propagation to a fixed point
     for (;;) {
-        if (t == 0) S.changed = 0;
+        if (t == 0) sChanged = 0;
         __syncthreads();
         for (int i = t; i < P; i += CL_THREADS) {
-            if (!((S.coremask[i >> 5] >> (i & 31)) & 1u)) continue;
-            int m = S.lab[i];
+            if (!((CORE[i >> 5] >> (i & 31)) & 1u)) continue;
+            int m = LAB[i];
             for (int w = 0; w * 32 < P; ++w) {
-                unsigned bits = S.adj[i][w] & S.coremask[w];
+                unsigned bits = ADJ[i * W + w] & CORE[w];
                 while (bits) {
                     const int j = w * 32 + __ffs(bits) - 1;
                     bits &= bits - 1;
-                    m = min(m, S.lab[j]);
+                    m = min(m, LAB[j]);
                 }
             }
-            if (m < S.lab[i]) { S.lab[i] = m; S.changed = 1; }
+            if (m < LAB[i]) { LAB[i] = m; sChanged = 1; }
         }
         __syncthreads();
-        if (!S.changed) break;
+        if (!sChanged) break;
         __syncthreads();
     }
     // ---- 4. border points: lowest-numbered cluster among the core neighbours
     for (int i = t; i < P; i += CL_THREADS) {
-        if ((S.coremask[i >> 5] >> (i & 31)) & 1u) continue;
+        if ((CORE[i >> 5] >> (i & 31)) & 1u) continue;
         int m = CL_BIG;
         for (int w = 0; w * 32 < P; ++w) {
-            unsigned bits = S.adj[i][w] & S.coremask[w];
+            unsigned bits = ADJ[i * W + w] & CORE[w];
             while (bits) {
                 const int j = w * 32 + __ffs(bits) - 1;
                 bits &= bits - 1;
-                m = min(m, S.lab[j]);
+                m = min(m, LAB[j]);
             }
         }
-        S.lab[i] = m;
+        LAB[i] = m;
     }
     __syncthreads();
     // ---- 5. number the clusters by their smallest core index (= sklearn's label order)
@@ -145,114 +183,127 @@ __global__ void __launch_bounds__(CL_THREADS) lidar_clusters_kernel(int R, const
         int base = 0;
         for (int c = 0; c < P; c += 32) {
             const int i = c + lane;
-            const bool root = i < P && S.lab[i] == i;
+            const bool root = i < P && LAB[i] == i;
             const unsigned m = __ballot_sync(0xffffffffu, root);
-            if (root) S.cid[i] = base + __popc(m & ((1u << lane) - 1u));
+            if (root) CID[i] = base + __popc(m & ((1u << lane) - 1u));
             base += __popc(m);
         }
-        if (lane == 0) S.n_clusters = base;
+        if (lane == 0) sNC = base;
     }
     __syncthreads();
-    for (int i = t; i < P; i += CL_THREADS)
-        labels[(size_t)b * R + S.ray[i]] = (S.lab[i] == CL_BIG) ? -1 : S.cid[S.lab[i]];
-    const int n_clusters = S.n_clusters;
+    const int n_clusters = sNC;
+    int ns = 32;                                   // sort size: next power of two >= P
+    while (ns < P) ns <<= 1;
+    // labels out; sort keys (cluster, x, y) for every point, noise and padding last
+    for (int i = t; i < ns; i += CL_THREADS) {
+        int c = CL_BIG;
+        double px = INFINITY, py = INFINITY;
+        if (i < P) {
+            if (LAB[i] != CL_BIG) c = CID[LAB[i]];
+            labels[(size_t)b * R + RAY[i]] = (c == CL_BIG) ? -1 : c;
+            px = X[i]; py = Y[i];
+        }
+        SC[i] = c; SX[i] = px; SY[i] = py;
+    }
+    if (t < CL_MAXC) { SEG0[t] = 0; SEGN[t] = 0; HN[t] = 0; }
+    __syncthreads();
 
-    // ---- 6. convex hull of every cluster
-    int n_out = 0;
-    bool ovf = false;
-    for (int c = 0; c < n_clusters; ++c) {
-        __syncthreads();
-        // gather the members (warp 0, index order)
-        if (t < 32) {
-            int base = 0;
-            for (int q = 0; q < P; q += 32) {
-                const int i = q + lane;
-                const bool in = i < P && S.lab[i] != CL_BIG && S.cid[S.lab[i]] == c;
-                const unsigned m = __ballot_sync(0xffffffffu, in);
-                if (in) { const int k = base + __popc(m & ((1u << lane) - 1u)); S.sx[k] = S.x[i]; S.sy[k] = S.y[i]; }
-                base += __popc(m);
-            }
-            if (lane == 0) S.cnt = base;
-        }
-        __syncthreads();
-        const int cnt = S.cnt;
-        int n2 = 1;
-        while (n2 < cnt) n2 <<= 1;
-        for (int i = cnt + t; i < n2; i += CL_THREADS) { S.sx[i] = INFINITY; S.sy[i] = INFINITY; }
-        __syncthreads();
-        // lexicographic bitonic sort (np.unique(points, axis=0) order)
-        for (int k = 2; k <= n2; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int i = t; i < n2; i += CL_THREADS) {
-                    const int l = i ^ j;
-                    if (l > i) {
-                        const bool up = (i & k) == 0;
-                        const double ax = S.sx[i], ay = S.sy[i], bx = S.sx[l], by = S.sy[l];
-                        if (lex_less(bx, by, ax, ay) == up) { S.sx[i] = bx; S.sy[i] = by; S.sx[l] = ax; S.sy[l] = ay; }
+    // ---- 6. ONE bitonic sort by (cluster, x, y): every cluster becomes a contiguous, np.unique-ordered segment
+    for (int k = 2; k <= ns; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = t; i < ns; i += CL_THREADS) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const int ac = SC[i], bc = SC[l];
+                    const double ax = SX[i], ay = SY[i], bx = SX[l], by = SY[l];
+                    if (key_less(bc, bx, by, ac, ax, ay) == up) {
+                        SC[i] = bc; SX[i] = bx; SY[i] = by; SC[l] = ac; SX[l] = ax; SY[l] = ay;
                     }
                 }
-                __syncthreads();
             }
+            __syncthreads();
         }
-        // duplicates out, collinearity test, monotone chain: sequential on <= 512 points (thread 0)
-        if (t == 0) {
-            int u = 0;
-            for (int i = 0; i < cnt; ++i)
-                if (u == 0 || S.sx[i] != S.sx[u - 1] || S.sy[i] != S.sy[u - 1]) { S.sx[u] = S.sx[i]; S.sy[u] = S.sy[i]; ++u; }
-            int h = 0;
-            if (u >= 3) {
-                // The reference drops a cluster when np.linalg.matrix_rank(points - points[0]) < 2 (`:75-76`) or when
-                // Qhull finds the input flat to its roundoff bound and raises (`:81-83`; ~23 eps max|coordinate|).  Both
-                // only ever trigger on readings taken on ONE straight edge (deviations ~1e-16); real corners deviate
-                // by >= 1e-6.  One test covers both: largest distance from the line through the lexicographic
-                // extremes <= 64 eps max|coordinate|.
-                const double dxl = S.sx[u - 1] - S.sx[0], dyl = S.sy[u - 1] - S.sy[0];
-                const double len = sqrt(dxl * dxl + dyl * dyl);
-                double maxdev = 0.0, scale = 0.0;
+    }
+    // segment boundaries
+    for (int i = t; i < ns; i += CL_THREADS) {
+        const int c = SC[i];
+        if (c < CL_MAXC) {
+            if (i == 0 || SC[i - 1] != c) SEG0[c] = i;
+            if (i == ns - 1 || SC[i + 1] != c) SEGN[c] = i + 1;        // end (exclusive)
+        }
+    }
+    __syncthreads();
+
+    // ---- 7. one thread per cluster: duplicates out, flatness test, Andrew's monotone chain (concurrently)
+    const int nc = min(n_clusters, CL_MAXC);
+    if (t < nc) {
+        const int s0 = SEG0[t], cnt = SEGN[t] - s0;
+        double* sx = SX + s0;
+        double* sy = SY + s0;
+        int* hull = HULL + s0 + t;               // cnt + 1 entries are enough; regions of different clusters are disjoint
+        int u = 0;
+        for (int i = 0; i < cnt; ++i)
+            if (u == 0 || sx[i] != sx[u - 1] || sy[i] != sy[u - 1]) { sx[u] = sx[i]; sy[u] = sy[i]; ++u; }
+        int h = 0;
+        if (u >= 3) {
+            // The reference drops a cluster when np.linalg.matrix_rank(points - points[0]) < 2 (`:75-76`) or when
+            // Qhull finds the input flat to its roundoff bound and raises (`:81-83`; ~23 eps max|coordinate|).  Both
+            // only ever trigger on readings taken on ONE straight edge (deviations ~1e-16); real corners deviate
+            // by >= 1e-6.  One test covers both: largest distance from the line through the lexicographic
+            // extremes <= 64 eps max|coordinate|.
+            const double dxl = sx[u - 1] - sx[0], dyl = sy[u - 1] - sy[0];
+            const double len = sqrt(dxl * dxl + dyl * dyl);
+            double maxdev = 0.0, scale = 0.0;
+            for (int i = 0; i < u; ++i) {
+                const double ex = sx[i] - sx[0], ey = sy[i] - sy[0];
+                maxdev = fmax(maxdev, fabs(dxl * ey - dyl * ex) / len);
+                scale = fmax(scale, fmax(fabs(sx[i]), fabs(sy[i])));
+            }
+            if (maxdev > 64.0 * 2.220446049250313e-16 * scale) {
                 for (int i = 0; i < u; ++i) {
-                    const double ex = S.sx[i] - S.sx[0], ey = S.sy[i] - S.sy[0];
-                    maxdev = fmax(maxdev, fabs(dxl * ey - dyl * ex) / len);
-                    scale = fmax(scale, fmax(fabs(S.sx[i]), fabs(S.sy[i])));
-                }
-                if (maxdev > 64.0 * 2.220446049250313e-16 * scale) {
-                    // Andrew's monotone chain, counter-clockwise, collinear points dropped
-                    for (int i = 0; i < u; ++i) {
-                        while (h >= 2) {
-                            const int a = S.hull[h - 2], bq = S.hull[h - 1];
-                            const double cr = (S.sx[bq] - S.sx[a]) * (S.sy[i] - S.sy[a]) - (S.sy[bq] - S.sy[a]) * (S.sx[i] - S.sx[a]);
-                            if (cr <= 0.0) --h; else break;
-                        }
-                        S.hull[h++] = i;
+                    while (h >= 2) {
+                        const int a = hull[h - 2], bq = hull[h - 1];
+                        const double cr = (sx[bq] - sx[a]) * (sy[i] - sy[a]) - (sy[bq] - sy[a]) * (sx[i] - sx[a]);
+                        if (cr <= 0.0) --h; else break;
                     }
-                    const int lower = h + 1;
-                    for (int i = u - 2; i >= 0; --i) {
-                        while (h >= lower) {
-                            const int a = S.hull[h - 2], bq = S.hull[h - 1];
-                            const double cr = (S.sx[bq] - S.sx[a]) * (S.sy[i] - S.sy[a]) - (S.sy[bq] - S.sy[a]) * (S.sx[i] - S.sx[a]);
-                            if (cr <= 0.0) --h; else break;
-                        }
-                        S.hull[h++] = i;
-                    }
-                    --h;                       // the last point repeats the first
-                    if (h < 3) h = 0;
+                    hull[h++] = i;
                 }
+                const int lower = h + 1;
+                for (int i = u - 2; i >= 0; --i) {
+                    while (h >= lower) {
+                        const int a = hull[h - 2], bq = hull[h - 1];
+                        const double cr = (sx[bq] - sx[a]) * (sy[i] - sy[a]) - (sy[bq] - sy[a]) * (sx[i] - sx[a]);
+                        if (cr <= 0.0) --h; else break;
+                    }
+                    hull[h++] = i;
+                }
+                --h;                       // the last point repeats the first
+                if (h < 3) h = 0;
             }
-            S.hull_n = h;
         }
-        __syncthreads();
-        const int h = S.hull_n;
-        if (h >= 3) {
-            if (n_out < max_hulls) {
-                const int hv = min(h, max_hull_verts);
-                if (h > max_hull_verts) ovf = true;
-                double2* dst = hull_verts + ((size_t)b * max_hulls + n_out) * max_hull_verts;
-                for (int i = t; i < max_hull_verts; i += CL_THREADS)
-                    dst[i] = (i < hv) ? make_double2(S.sx[S.hull[i]], S.sy[S.hull[i]]) : make_double2(0.0, 0.0);
-                if (t == 0) hull_nverts[(size_t)b * max_hulls + n_out] = hv;
-                ++n_out;
-            } else {
-                ovf = true;
-            }
+        HN[t] = h;
+    }
+    __syncthreads();
+
+    // ---- 8. write the hulls in cluster order (clusters without a hull are skipped)
+    int n_out = 0;
+    bool ovf = n_clusters > CL_MAXC;
+    for (int c = 0; c < nc; ++c) {
+        const int h = HN[c];
+        if (h < 3) continue;
+        if (n_out < max_hulls) {
+            const int hv = min(h, max_hull_verts);
+            if (h > max_hull_verts) ovf = true;
+            const int s0 = SEG0[c];
+            const int* hull = HULL + s0 + c;
+            double2* dst = hull_verts + ((size_t)b * max_hulls + n_out) * max_hull_verts;
+            for (int i = t; i < max_hull_verts; i += CL_THREADS)
+                dst[i] = (i < hv) ? make_double2(SX[s0 + hull[i]], SY[s0 + hull[i]]) : make_double2(0.0, 0.0);
+            if (t == 0) hull_nverts[(size_t)b * max_hulls + n_out] = hv;
+            ++n_out;
+        } else {
+            ovf = true;
         }
     }
     for (int o = n_out + t; o < max_hulls; o += CL_THREADS) hull_nverts[(size_t)b * max_hulls + o] = 0;
@@ -270,7 +321,7 @@ extern "C" int ldcbf_lidar_clusters_f64(int B, int R, const double* hit_xy, cons
     if (B == 0) return LDCBF_OK;
     if (!hit_xy || !labels || !hull_verts || !hull_nverts || !n_hulls) return LDCBF_E_ARG;
     if (R > CL_RMAX) return LDCBF_E_SHAPE;
-    const size_t smem = sizeof(ClusterShared);
+    const size_t smem = ClusterLayout(R).bytes + 64;
     cudaError_t e = cudaFuncSetAttribute(lidar_clusters_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_last_error(e); return LDCBF_E_LAUNCH; }
     lidar_clusters_kernel<<<B, CL_THREADS, smem, static_cast<cudaStream_t>(cuda_stream)>>>(
