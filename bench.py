@@ -282,6 +282,7 @@ def run_ours(args):
             line["lidar"] = lidar_bench(L, flush, peak_fp64, torch)
             line["unknown_env"] = unknown_env_bench(L, flush, torch)
             line["latency_b1"] = latency_b1(L, torch)
+            line["bounds_tuning"] = bounds_tuning_bench(torch)
     if rank == 0:
         line["clocks"] = clk.summary()
         if port is not None:
@@ -446,6 +447,20 @@ def latency_b1(L, torch, n=200):
             tw.append((time.perf_counter() - t0) * 1e6)
     return {"p50_device_us": statistics.median(ts), "p50_wall_us": statistics.median(tw),
             "note": "B=1, config 1 step 0; reference: CasADi/IPOPT per step, not measurable offline"}
+
+
+def bounds_tuning_bench(torch):
+    """The reference's own batch workload (report_simulations/bounds_tuning.py: 26 880 closed-loop simulations run one
+    after the other) as ONE rollout launch with per-scenario limits."""
+    from HumanoidNavigation.report_simulations.bounds_tuning import bounds_tuning
+    bounds_tuning()                                   # warm-up (allocations)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    best, res, score, steps = bounds_tuning(return_all=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"simulations": int(len(score)), "seconds": dt, "mpc_solves": int(steps.sum() // 4),
+            "best_combination": [float(v) for v in best], "best_res": res}
 
 
 def e2e(L, sc, foots, args, torch):

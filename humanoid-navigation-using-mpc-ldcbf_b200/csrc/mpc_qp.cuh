@@ -94,6 +94,24 @@ struct QpSolution {
     int status, iters;
 };
 
+// Per-scenario limits (defaults from ldcbf_params, optionally overridden by the `limits` array of the ABI:
+// limits[b] = (ALPHA, V_MAX[0], V_MAX[1], OMEGA_MAX, OMEGA_MIN, reserved), NaN = keep the default).
+struct Limits {
+    double alpha_over_pi, vmax0, vmax1, omega_max, omega_min;
+};
+LDCBF_HD Limits load_limits(const StepConst& C, const double* limits, size_t b) {
+    Limits L{C.alpha_over_pi, C.v_max0, C.v_max1, C.omega_max, C.omega_min};
+    if (limits) {
+        const double* q = limits + 6 * b;
+        if (q[0] == q[0]) L.alpha_over_pi = q[0] / 3.141592653589793;
+        if (q[1] == q[1]) L.vmax0 = q[1];
+        if (q[2] == q[2]) L.vmax1 = q[2];
+        if (q[3] == q[3]) L.omega_max = q[3];
+        if (q[4] == q[4]) L.omega_min = q[4];
+    }
+    return L;
+}
+
 // Row identifiers: leg(k,sub) = 2k+sub (k<N); vel(k,sub) = 2N + 2(k-1) + sub (k=1..N);
 // cbf(k,o) = 4N + (k-1)*MO + o (k=1..N).  A candidate is (id, sg): sg=+1 means a.w >= lo, -1 means -a.w >= -hi.
 //
@@ -159,6 +177,7 @@ struct QpState {
     int ns;                               // how many of them
     double delta;
     double vmid[N + 1], vhalf[N + 1];     // merged longitudinal velocity row at state k: mid +- half
+    double vlat_mid, vlat_half;           // lateral velocity row: [V_MIN1, V_MAX1]
     double p0x, p0y, v0x, v0y, gx, gy;
     double px[N + 1], py[N + 1];          // current iterate w = (p_1..p_N), p_0 fixed
     double u[2 * N];                      // multipliers per slot
@@ -176,8 +195,9 @@ struct QpState {
 template <int N, int MO, int WS>
 LDCBF_HD void qp_setup(const StepConst& C, double p0x, double v0x, double p0y, double v0y, double th0, double gx,
                        double gy, const int (&ft)[N + 1], const double4 (&ce)[MO], int nb, const double4* ce_stream,
-                       int n_stream, double delta, double alpha_over_pi, double vmax0, double omega_max,
-                       double omega_min, double* ws, QpState<N, MO>& s) {
+                       int n_stream, double delta, const Limits& lim, double* ws, QpState<N, MO>& s) {
+    const double alpha_over_pi = lim.alpha_over_pi, vmax0 = lim.vmax0, omega_max = lim.omega_max, omega_min = lim.omega_min;
+    s.vlat_mid = 0.5 * (lim.vmax1 + C.v_min1); s.vlat_half = 0.5 * (lim.vmax1 - C.v_min1);
     constexpr int NV = 2 * N;
     s.p0x = p0x; s.p0y = p0y; s.v0x = v0x; s.v0y = v0y; s.gx = gx; s.gy = gy; s.nb = nb;
     s.ces = ce_stream; s.ns = n_stream; s.delta = delta;
@@ -281,8 +301,8 @@ LDCBF_HD void qp_trip(const StepConst& C, double* ws, QpState<N, MO>& s) {
                 m = (s.rc[kk] * Vx + s.rs[kk] * Vy) - s.vmid[kk];
                 sl[2 * N + 2 * k] = s.vhalf[kk] - fabs(m);
                 upper |= nonneg_bit(m) << (2 * N + 2 * k);
-                m = ((double)s.ft[kk] * s.rc[kk] * Vy - s.rs[kk] * Vx) - C.vlat_mid;
-                sl[2 * N + 2 * k + 1] = C.vlat_half - fabs(m);
+                m = ((double)s.ft[kk] * s.rc[kk] * Vy - s.rs[kk] * Vx) - s.vlat_mid;
+                sl[2 * N + 2 * k + 1] = s.vlat_half - fabs(m);
                 upper |= nonneg_bit(m) << (2 * N + 2 * k + 1);
 #pragma unroll
                 for (int o = 0; o < MO; ++o)
@@ -458,11 +478,9 @@ LDCBF_HD void qp_finish(const StepConst& C, const QpState<N, MO>& s, QpSolution<
 template <int N, int MO, int WS>
 LDCBF_HD void solve_scenario(const StepConst& C, double p0x, double v0x, double p0y, double v0y, double th0, double gx,
                              double gy, const int (&ft)[N + 1], const double4 (&ce)[MO], int nb, const double4* ce_stream,
-                             int n_stream, double delta, double alpha_over_pi, double vmax0, double omega_max,
-                             double omega_min, double* ws, QpSolution<N>& S) {
+                             int n_stream, double delta, const Limits& lim, double* ws, QpSolution<N>& S) {
     QpState<N, MO> s;
-    qp_setup<N, MO, WS>(C, p0x, v0x, p0y, v0y, th0, gx, gy, ft, ce, nb, ce_stream, n_stream, delta, alpha_over_pi, vmax0,
-                        omega_max, omega_min, ws, s);
+    qp_setup<N, MO, WS>(C, p0x, v0x, p0y, v0y, th0, gx, gy, ft, ce, nb, ce_stream, n_stream, delta, lim, ws, s);
     while (!s.done) qp_trip<N, MO, WS>(C, ws, s);
     qp_finish<N, MO>(C, s, S);
 }

@@ -59,18 +59,6 @@ __device__ __forceinline__ void store_solution(const QpSolution<N>& S, int b, co
     io.iters[b] = S.iters;
 }
 
-__device__ __forceinline__ void load_limits(const StepConst& C, const double* limits, int b, double& aop,
-                                            double& vmax0, double& omax, double& omin) {
-    aop = C.alpha_over_pi; vmax0 = C.v_max0; omax = C.omega_max; omin = C.omega_min;
-    if (limits) {
-        const double4 L = reinterpret_cast<const double4*>(limits)[b];
-        if (L.x == L.x) aop = L.x / 3.141592653589793;
-        if (L.y == L.y) vmax0 = L.y;
-        if (L.z == L.z) omax = L.z;
-        if (L.w == L.w) omin = L.w;
-    }
-}
-
 // One thread per scenario; BLOCK threads per block (32 for small batches so the warps spread over all SMs, 128
 // otherwise).  Dynamic shared memory: QpWorkspace<N>::DOUBLES doubles per thread, element-major.
 template <int N, int MO, int BLOCK>
@@ -85,8 +73,7 @@ __global__ void __launch_bounds__(BLOCK) mpc_qp_kernel(StepConst C, int B, int m
     int ft[N + 1];
 #pragma unroll
     for (int k = 0; k <= N; ++k) ft[k] = io.foot[(size_t)b * (N + 1) + k];
-    double aop, vmax0, omax, omin;
-    load_limits(C, io.limits, b, aop, vmax0, omax, omin);
+    const Limits lim = load_limits(C, io.limits, (size_t)b);
     const int nt = min(io.nobs[b], max_obs);
     const int nb = min(nt, MO);
     double4 ce[MO];
@@ -95,7 +82,7 @@ __global__ void __launch_bounds__(BLOCK) mpc_qp_kernel(StepConst C, int B, int m
     for (int o = 0; o < MO; ++o) ce[o] = (o < nb) ? gce[o] : make_double4(0.0, 0.0, 0.0, 0.0);
     QpSolution<N> S;
     solve_scenario<N, MO, BLOCK>(C, x.x, x.y, x.z, x.w, th0, g.x, g.y, ft, ce, nb, gce + MO, nt - nb,
-                                 io.delta ? io.delta[b] : 0.0, aop, vmax0, omax, omin, qp_ws + threadIdx.x, S);
+                                 io.delta ? io.delta[b] : 0.0, lim, qp_ws + threadIdx.x, S);
     store_solution<N>(S, b, io);
 }
 
@@ -144,8 +131,7 @@ __global__ void __launch_bounds__(BLOCK) mpc_qp_refill_kernel(StepConst C, int B
                     int ft[N + 1];
 #pragma unroll
                     for (int k = 0; k <= N; ++k) ft[k] = io.foot[(size_t)b * (N + 1) + k];
-                    double aop, vmax0, omax, omin;
-                    load_limits(C, io.limits, b, aop, vmax0, omax, omin);
+                    const Limits lim = load_limits(C, io.limits, (size_t)b);
                     const int nt = min(io.nobs[b], max_obs);
                     const int nb = min(nt, MO);
                     double4 ce[MO];
@@ -153,7 +139,7 @@ __global__ void __launch_bounds__(BLOCK) mpc_qp_refill_kernel(StepConst C, int B
 #pragma unroll
                     for (int o = 0; o < MO; ++o) ce[o] = (o < nb) ? gce[o] : make_double4(0.0, 0.0, 0.0, 0.0);
                     qp_setup<N, MO, BLOCK>(C, x.x, x.y, x.z, x.w, th0, g.x, g.y, ft, ce, nb, gce + MO, nt - nb,
-                                           io.delta ? io.delta[b] : 0.0, aop, vmax0, omax, omin, ws, s);
+                                           io.delta ? io.delta[b] : 0.0, lim, ws, s);
                 }
                 next = min(end, next + __popc(free_m));
             }

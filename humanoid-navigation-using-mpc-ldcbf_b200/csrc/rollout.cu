@@ -34,15 +34,7 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
     const bool right_first = io.right_first[b] != 0;
     const int nb = min(io.nobs[b], MO);
     const double dl = io.delta ? io.delta[b] : 0.0;
-    double aop, vmax0, omax, omin;
-    aop = C.alpha_over_pi; vmax0 = C.v_max0; omax = C.omega_max; omin = C.omega_min;
-    if (io.limits) {
-        const double4 L = reinterpret_cast<const double4*>(io.limits)[b];
-        if (L.x == L.x) aop = L.x / 3.141592653589793;
-        if (L.y == L.y) vmax0 = L.y;
-        if (L.z == L.z) omax = L.z;
-        if (L.w == L.w) omin = L.w;
-    }
+    const Limits lim = load_limits(C, io.limits, (size_t)b);
     double* tX = io.traj_X ? io.traj_X + (size_t)b * (T + 1) * 5 : nullptr;
     double* tU = io.traj_U ? io.traj_U + (size_t)b * T * 3 : nullptr;
     if (tX) { tX[0] = px; tX[1] = vx; tX[2] = py; tX[3] = vy; tX[4] = th; }
@@ -75,7 +67,7 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
 #pragma unroll
             for (int k = 0; k <= N; ++k) ft[k] = (((step_number + k) & 1) == (right_first ? 0 : 1)) ? 1 : -1;
             QpSolution<N> S;
-            solve_scenario<N, MO, BLOCK>(C, px, vx, py, vy, th, gx, gy, ft, ce, nb, nullptr, 0, dl, aop, vmax0, omax, omin,
+            solve_scenario<N, MO, BLOCK>(C, px, vx, py, vy, th, gx, gy, ft, ce, nb, nullptr, 0, dl, lim,
                                          qp_ws + threadIdx.x, S);
             ++solves;
             last_status = S.status;
@@ -96,7 +88,7 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
         } else {
             // sub-step: only the heading advances (:443-447)
             const double phi = atan2(gy - py, gx - px);
-            om0 = fmin(fmax(phi - th, omin), omax);
+            om0 = fmin(fmax(phi - th, lim.omega_min), lim.omega_max);
             th1 = __dadd_rn(th, __dmul_rn(om0, C.sampling_time));
         }
         th = th1;

@@ -73,8 +73,8 @@ typedef struct ldcbf_params {
 #define LDCBF_FLAG_FAST_GEOMETRY 1
 
 /* Optional per-scenario overrides of the limits `bounds_tuning.py:22-26` mutates:
- * limits[b] = (ALPHA, V_MAX[0], OMEGA_MAX, OMEGA_MIN).  NaN entries fall back to ldcbf_params. */
-#define LDCBF_LIMITS_STRIDE 4
+ * limits[b] = (ALPHA, V_MAX[0], V_MAX[1], OMEGA_MAX, OMEGA_MIN, reserved).  NaN entries fall back to ldcbf_params. */
+#define LDCBF_LIMITS_STRIDE 6
 
 int ldcbf_abi_version(void);
 void ldcbf_params_default(ldcbf_params* prm);
@@ -98,7 +98,7 @@ int ldcbf_halfplanes_f64(int B, int max_obs, int max_verts, const double* pos, c
  * :252-294, :321-333), optim_prob.solve() (:417) and _integrate (:335-343, :441-447).
  *   x0 [B,4], theta0 [B], goal [B,2], foot [B,N+1] int8 (+1 right / -1 left, the s_v window of :403)
  *   c_eta [B,max_obs,4], nobs [B]; delta [B] or NULL (HumanoidMPCCustomLCBF.py:30-31);
- *   limits [B,4] or NULL
+ *   limits [B,6] or NULL
  * out: U [B,N,2] footsteps, X [B,N+1,4] predicted states (X[:,1] is the next state), theta [B,N+1],
  *      omega [B,N], obj [B] (value of the reference's cost incl. the constant k=0 term), status [B], iters [B].
  * For status != 0 the U, X, obj entries are NaN. */

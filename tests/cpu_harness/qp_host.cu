@@ -25,8 +25,8 @@ extern "C" int qp_host_solve_n3(const ldcbf_params* prm, int B, int max_obs, con
         solve_scenario<N, MO, 1>(C, x0[4 * b], x0[4 * b + 1], x0[4 * b + 2], x0[4 * b + 3], theta0[b], goal[2 * b],
                               goal[2 * b + 1], ft, ce, nb,
                                  reinterpret_cast<const double4*>(c_eta + ((size_t)b * max_obs + MO) * 4),
-                                 (nobs[b] < max_obs ? nobs[b] : max_obs) - nb, delta ? delta[b] : 0.0, C.alpha_over_pi, C.v_max0,
-                              C.omega_max, C.omega_min, ws, S);
+                                 (nobs[b] < max_obs ? nobs[b] : max_obs) - nb, delta ? delta[b] : 0.0,
+                                 load_limits(C, nullptr, 0), ws, S);
         for (int k = 0; k < N; ++k) { U[(b * N + k) * 2] = S.ux[k]; U[(b * N + k) * 2 + 1] = S.uy[k]; omega[b * N + k] = S.om[k]; }
         for (int k = 0; k <= N; ++k) {
             double* x = X + ((size_t)b * (N + 1) + k) * 4;

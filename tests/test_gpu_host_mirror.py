@@ -148,3 +148,31 @@ def test_known_crowded_map_runs_stepwise_with_twenty_obstacles():
     X, U, _ = m.run_simulation(None, make_fast_plot=False, fill_animator=False)
     assert U.shape[1] >= 10
     check_run(X, U, (4, 3.5), rings, 0.4, delta=1e-6, N_simul=80)
+
+
+def test_bounds_tuning_grid_in_one_launch():
+    """A slice of the reference's hyper-parameter grid (bounds_tuning.py:17-26): every combination is one scenario of a
+    single rollout launch; each run is checked against the oracle's closed loop under the same mutated `conf`."""
+    from HumanoidNavigation.report_simulations.bounds_tuning import bounds_tuning, hyperparameter_grid
+    grid = hyperparameter_grid()
+    assert grid.shape == (26880, 4)
+    sub = grid[::2689][:10]
+    (best, best_res, score, steps) = bounds_tuning(grid=sub, N_mpc_timesteps=40, return_all=True)
+    assert len(score) == len(sub) and (steps >= 0).all() and (steps > 0).sum() >= 8     # a combination may be infeasible at step 0
+    # oracle for two of them: first 6 MPC steps (24 loop iterations) agree
+    import ldcbf_b200
+    for i in (0, 7):
+        conf = model.default_conf()
+        conf["V_MAX"], conf["ALPHA"], conf["OMEGA_MAX"], conf["OMEGA_MIN"] = [sub[i][0], sub[i][1]], sub[i][2], sub[i][3], -sub[i][3]
+        Xo, Uo = mpc.run_simulation((5, 5), [], (0, 0, 0, 0, 0), 3, 40, 0.1, conf=conf)
+        from HumanoidNavigation.MPC import HumanoidMpc
+        saved = dict(HumanoidMpc.conf)
+        try:
+            HumanoidMpc.conf.update(ALPHA=sub[i][2], V_MAX=[sub[i][0], sub[i][1]], OMEGA_MAX=sub[i][3], OMEGA_MIN=-sub[i][3])
+            m = HumanoidMpc.HumanoidMPC(N_horizon=3, N_mpc_timesteps=40, sampling_time=0.1, goal=(5, 5),
+                                        init_state=(0, 0, 0, 0, 0), obstacles=[], verbosity=0)
+            X, U, _ = m.run_simulation(None, make_fast_plot=False, fill_animator=False)
+        finally:
+            HumanoidMpc.conf.clear(); HumanoidMpc.conf.update(saved)
+        n = min(24, X.shape[1], Xo.shape[1])
+        np.testing.assert_allclose(X[:, :n], Xo[:, :n], atol=1e-6)

@@ -172,9 +172,10 @@ def test_many_obstacles_and_per_scenario_limits(L):
     states, goals = np.array(states), np.array(goals)
     foots = scenarios.foot_window(np.ones(B, bool), 0, 3)
     verts, nverts, nobs = scenarios.pack_rings(rings_all, 8, 11)
-    limits = np.full((B, 4), np.nan)
-    limits[::2] = np.column_stack((rs.uniform(1.0, 4.0, B // 2), rs.uniform(0.5, 0.9, B // 2),
-                                   rs.uniform(0.2, 0.6, B // 2), -rs.uniform(0.2, 0.6, B // 2)))
+    limits = np.full((B, 6), np.nan)          # (ALPHA, V_MAX[0], V_MAX[1], OMEGA_MAX, OMEGA_MIN, reserved)
+    limits[::2, :5] = np.column_stack((rs.uniform(1.0, 4.0, B // 2), rs.uniform(0.5, 0.9, B // 2),
+                                       rs.uniform(0.25, 0.45, B // 2), rs.uniform(0.2, 0.6, B // 2),
+                                       -rs.uniform(0.2, 0.6, B // 2)))
     prm = L.default_params(0.4)
     out = L.mpc_step(prm, cu(states[:, :4]), cu(states[:, 4]), cu(goals), cu(foots, torch.int8), cu(verts),
                      cu(nverts, torch.int32), cu(nobs, torch.int32), limits=cu(limits))
@@ -183,8 +184,8 @@ def test_many_obstacles_and_per_scenario_limits(L):
     for b in range(B):
         conf = model.default_conf()
         if b % 2 == 0:
-            conf["ALPHA"], conf["V_MAX"], conf["OMEGA_MAX"], conf["OMEGA_MIN"] = (limits[b, 0], [limits[b, 1], 0.4],
-                                                                                  limits[b, 2], limits[b, 3])
+            conf["ALPHA"], conf["V_MAX"], conf["OMEGA_MAX"], conf["OMEGA_MIN"] = (limits[b, 0], [limits[b, 1], limits[b, 2]],
+                                                                                  limits[b, 3], limits[b, 4])
         r = mpc.mpc_step(states[b], goals[b], rings_all[b], [int(v) for v in foots[b]], sampling_time=0.4, conf=conf)
         assert out["status"][b] == r["status"], b
         if r["status"] == 0:
