@@ -5,55 +5,33 @@
 //   Utils/ObstaclesUtils.py:50-57   is_point_inside_polygon (matplotlib Path.contains_point)
 //   MPC/HumanoidMpc.py:296-319      _get_list_c_and_eta
 //
-// Mapping: one thread per (scenario, obstacle) pair.  A block of 64 threads first stages the vertex rings of
-// its 64 consecutive pairs into shared memory with coalesced 16-byte loads (only the nverts valid vertices of
-// each ring are touched, so DRAM traffic is the algorithmic 16*E bytes), then every thread walks its own ring
-// serially: no shuffles, no idle lanes inside a ring, one LDS.128 per edge.  Rings are stored with an odd
-// stride (in 16-byte units) so the 32 lanes of a warp hit 32 different bank groups.
-// 16*E bytes in and 32 bytes out per obstacle against ~95 (bit-exact arithmetic) / ~50 (fast arithmetic)
-// instructions per edge: see DESIGN.md §6 for where that puts the kernel between the HBM and FP64 rooflines.
-#include <cuda_pipeline.h>
-
+// Mapping: one thread per (scenario, obstacle) pair walks its own ring of double2 vertices straight from global
+// memory (16-byte __ldg loads; a 128-byte line serves 8 consecutive edges of the same thread and stays in L1 in
+// between).  No shuffles, no idle lanes inside a ring, DRAM traffic = the valid vertices only.
+// An earlier version staged the rings of a block in shared memory with coalesced cp.async copies; it was 1.5x
+// slower (0.58 vs 0.39 ms at B = 2^20): the 400 B of shared memory per thread capped the SM at 16 warps, and this
+// kernel needs warps more than it needs coalescing — the bit-exact arithmetic costs ~95 instructions per edge
+// (two square roots, one division), so it sits between the HBM and the FP64-issue rooflines.
 #include "halfplane_dev.cuh"
 
 namespace ldcbf {
 
-constexpr int K1_THREADS = 64;
+constexpr int K1_THREADS = 128;
 
 template <bool EXACT>
-__global__ void __launch_bounds__(K1_THREADS) halfplane_kernel(int n_pairs, int max_obs, int max_verts, int sstride,
+__global__ void __launch_bounds__(K1_THREADS) halfplane_kernel(int n_pairs, int max_obs, int max_verts,
                                                                const double* __restrict__ pos, int pos_stride,
                                                                int y_off, const double2* __restrict__ verts,
                                                                const int32_t* __restrict__ nverts,
                                                                const int32_t* __restrict__ nobs,
                                                                double4* __restrict__ c_eta) {
-    extern __shared__ double2 srings[];                 // [K1_THREADS][sstride]
-    __shared__ int sV[K1_THREADS];
-    const int pair0 = blockIdx.x * K1_THREADS;
-    const int pair = pair0 + threadIdx.x;
-    int V = 0, b = 0;
-    if (pair < n_pairs) {
-        b = pair / max_obs;
-        const int o = pair - b * max_obs;
-        V = (o < nobs[b]) ? min(nverts[pair], max_verts) : 0;
-    }
-    sV[threadIdx.x] = V;
-    __syncthreads();
-    // coalesced staging of the block's contiguous vertex range
-    const double2* g = verts + (size_t)pair0 * max_verts;
-    const int total = K1_THREADS * max_verts;
-    // cp.async (LDGSTS): all of a thread's 16-byte copies are in flight at once, no register staging
-    for (int i = threadIdx.x; i < total; i += K1_THREADS) {
-        const int lp = i / max_verts, e = i - lp * max_verts;
-        if (e < sV[lp]) __pipeline_memcpy_async(srings + lp * sstride + e, g + i, sizeof(double2));
-    }
-    __pipeline_commit();
-    __pipeline_wait_prior(0);
-    __syncthreads();
+    const int pair = blockIdx.x * K1_THREADS + threadIdx.x;
     if (pair >= n_pairs) return;
+    const int b = pair / max_obs, o = pair - b * max_obs;
+    const int V = (o < nobs[b]) ? min(nverts[pair], max_verts) : 0;
     if (V <= 0) { c_eta[pair] = make_double4(0.0, 0.0, 0.0, 0.0); return; }
     const double px = pos[(size_t)b * pos_stride], py = pos[(size_t)b * pos_stride + y_off];
-    c_eta[pair] = halfplane_serial<EXACT>(px, py, srings + threadIdx.x * sstride, V);
+    c_eta[pair] = halfplane_serial<EXACT>(px, py, verts + (size_t)pair * max_verts, V);
 }
 
 // Small-batch variant: G lanes per (scenario, obstacle) pair, lane l takes edges l, l+G, ...  With a few thousand
@@ -117,18 +95,11 @@ int launch_halfplanes(int B, int max_obs, int max_verts, const double* pos, int 
             halfplane_split_kernel<true, 8><<<grid, 128, 0, st>>>(n_pairs, max_obs, max_verts, pos, pos_stride, y_off, v2, nverts, nobs, ce);
         return check_launch();
     }
-    const int sstride = max_verts | 1;                                  // odd stride in 16-byte units
-    const size_t smem = (size_t)K1_THREADS * sstride * sizeof(double2);
-    if (smem > 200 * 1024) return LDCBF_E_SHAPE;
-    auto kern = fast_geometry ? halfplane_kernel<false> : halfplane_kernel<true>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_last_error(e); return LDCBF_E_LAUNCH; }
-    }
     const unsigned grid = (unsigned)((n_pairs + K1_THREADS - 1) / K1_THREADS);
-    kern<<<grid, K1_THREADS, smem, st>>>(n_pairs, max_obs, max_verts, sstride, pos, pos_stride, y_off,
-                                         reinterpret_cast<const double2*>(verts), nverts, nobs,
-                                         reinterpret_cast<double4*>(c_eta));
+    auto kern = fast_geometry ? halfplane_kernel<false> : halfplane_kernel<true>;
+    kern<<<grid, K1_THREADS, 0, st>>>(n_pairs, max_obs, max_verts, pos, pos_stride, y_off,
+                                      reinterpret_cast<const double2*>(verts), nverts, nobs,
+                                      reinterpret_cast<double4*>(c_eta));
     return check_launch();
 }
 
