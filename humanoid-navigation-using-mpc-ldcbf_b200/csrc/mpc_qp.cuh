@@ -163,7 +163,7 @@ LDCBF_HD void row_normal(int id, double sg, double gtil, const double (&rc)[N + 
 // (consecutive threads -> consecutive 8-byte words: conflict-free); a slot is then written with a dynamic
 // address instead of a chain of predicated register moves, and ~110 registers are freed.
 template <int N>
-struct QpWorkspace { static constexpr int DOUBLES = 2 * (2 * N) * (2 * N); };
+struct QpWorkspace { static constexpr int DOUBLES = 2 * (2 * N) * (2 * N) + 2 * N; };   // normals, Gram, row code per slot
 
 // Solver state of one scenario, kept in registers across trips of the active-set loop.
 template <int N, int MO>
@@ -182,6 +182,7 @@ struct QpState {
     double px[N + 1], py[N + 1];          // current iterate w = (p_1..p_N), p_0 fixed
     double u[2 * N];                      // multipliers per slot
     double np[2 * N], nn, s_p, u_p;       // row being added: signed normal, |n|^2, slack, multiplier
+    int p_code;                           // ... and its row code 2*id + (upper side)
     unsigned amask;                       // occupied slots
     int status, iters;
     bool need_scan, done;
@@ -189,6 +190,7 @@ struct QpState {
 
 #define AN(j, i) ws[((j) * NV + (i)) * WS]
 #define GM(i, j) ws[(NV * NV + (i) * NV + (j)) * WS]
+#define RC(j) ws[(2 * NV * NV + (j)) * WS]      // row code of slot j: 2*id + (1 if the upper side), as a double
 
 // Heading schedule, half-plane offsets, row bounds, unconstrained optimum, empty active set.
 // ce[o] = (c_x, c_y, eta_x, eta_y) for o < nb.
@@ -256,8 +258,9 @@ LDCBF_HD void qp_setup(const StepConst& C, double p0x, double v0x, double p0y, d
         s.u[j] = 0.0; s.np[j] = 0.0;
 #pragma unroll
         for (int i = 0; i < NV; ++i) { AN(j, i) = 0.0; GM(j, i) = (i == j) ? 1.0 : 0.0; }
+        RC(j) = -1.0;
     }
-    s.nn = 1.0; s.s_p = 0.0; s.u_p = 0.0;
+    s.nn = 1.0; s.s_p = 0.0; s.u_p = 0.0; s.p_code = 0;
     s.iters = 0;
     s.need_scan = true;
     s.status = status;
@@ -341,6 +344,7 @@ LDCBF_HD void qp_trip(const StepConst& C, double* ws, QpState<N, MO>& s) {
 #pragma unroll
         for (int i = 0; i < NV; ++i) nn += s.np[i] * s.np[i];
         s.nn = nn; s.s_p = best; s.u_p = 0.0;
+        s.p_code = 2 * bid + (bsg < 0.0 ? 1 : 0);
         s.need_scan = false;
     }
     if (++s.iters > C.max_iter) { s.status = LDCBF_STATUS_MAX_ITER; s.done = true; return; }
@@ -435,10 +439,187 @@ LDCBF_HD void qp_trip(const StepConst& C, double* ws, QpState<N, MO>& s) {
             gcol[l * NV * WS] = val;
         }
         grow[slot * WS] = full ? s.nn : 1.0;
+        (&RC(0))[slot * WS] = full ? (double)s.p_code : -1.0;
     }
 }
+
+// Warm start of the dual active-set method from a guessed active set (closed loop: the final active set of the
+// previous MPC step shifted by one stage, `shift_codes`).  Goldfarb-Idnani may start from any point that is the
+// optimum of the equality-constrained problem on a set of independent rows with non-negative multipliers, so:
+// load the guessed rows into the slots, u = G^-1 (b - N^T g) (one Cholesky), drop every row with u_j < 0 and solve
+// again (at most NV rounds), w = g + N u.  A guess that turns out dependent falls back to the cold start.  The
+// result is exact whatever the guess; a good guess replaces ~15 trips by 2-4.
+// codes[j] = 2*id + (upper side) or -1.  Must be called right after qp_setup (w = g, empty active set).
+template <int N, int MO, int WS>
+LDCBF_HD void qp_warm_start(const StepConst& C, const int (&codes)[2 * N], double* ws, QpState<N, MO>& s) {
+    constexpr int NV = 2 * N;
+    if (s.done) return;
+    // signed deviations m = v - mid of all two-sided rows and slacks of the LDCBF rows at w = g (same formulas as
+    // the scan), to turn a row code into its right-hand side: b - n.g = -(slack of that side at g)
+    double mdev[4 * N], half[4 * N], cbf[N * MO];
+    {
+        double Vx = s.v0x, Vy = s.v0y;
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const double dx = s.px[k + 1] - s.px[k], dy = s.py[k + 1] - s.py[k];
+            const double off = (double)s.ft[k] * C.foot_offset;
+            mdev[2 * k] = (s.rc[k] * dx + s.rs[k] * dy) - C.legx_mid;          half[2 * k] = C.legx_half;
+            mdev[2 * k + 1] = (s.rc[k] * dy - s.rs[k] * dx) - (C.legy_mid - off); half[2 * k + 1] = C.legy_half;
+            Vx = C.gtil * dx - Vx; Vy = C.gtil * dy - Vy;
+            const int kk = k + 1;
+            mdev[2 * N + 2 * k] = (s.rc[kk] * Vx + s.rs[kk] * Vy) - s.vmid[kk]; half[2 * N + 2 * k] = s.vhalf[kk];
+            mdev[2 * N + 2 * k + 1] = ((double)s.ft[kk] * s.rc[kk] * Vy - s.rs[kk] * Vx) - s.vlat_mid;
+            half[2 * N + 2 * k + 1] = s.vlat_half;
+#pragma unroll
+            for (int o = 0; o < MO; ++o) cbf[k * MO + o] = s.ex[o] * s.px[kk] + s.ey[o] * s.py[kk] - s.hb[o];
+        }
+    }
+    double rhs[NV];
+    unsigned mask = 0;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        rhs[j] = 0.0;
+        const int code = codes[j];
+        const int id = code >> 1;
+        bool ok = code >= 0 && id < 4 * N + N * MO;
+        double sl = 0.0;
+        const double sg = (code & 1) ? -1.0 : 1.0;
+        if (ok) {
+            if (id < 4 * N) {
+                double m = 0.0, h = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4 * N; ++i) if (i == id) { m = mdev[i]; h = half[i]; }
+                sl = h + sg * m;                      // lower side: v - lo = half + m ; upper side: hi - v = half - m
+            } else {
+                const int q = id - 4 * N;
+                ok = (q % MO) < s.nb && !(code & 1);
+#pragma unroll
+                for (int i = 0; i < N * MO; ++i) if (i == q) sl = cbf[i];
+            }
+        }
+        if (ok) {
+            double a[NV];
+            row_normal<N, MO>(id, sg, C.gtil, s.rc, s.rs, s.ft, s.ex, s.ey, s.ces, s.ns, a);
+#pragma unroll
+            for (int i = 0; i < NV; ++i) AN(j, i) = a[i];
+            RC(j) = (double)code;
+            rhs[j] = -sl;
+            mask |= 1u << j;
+        }
+    }
+    if (mask == 0u) return;
+    bool fail = false;
+    double uu[NV];
+    for (int round = 0; round <= NV; ++round) {
+        // Gram matrix of the loaded slots (identity on the empty ones), Cholesky, u = G^-1 rhs
+        double L[NV][NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const bool aj = (mask >> j) & 1u;
+#pragma unroll
+            for (int l = 0; l <= j; ++l) {
+                double g2 = 0.0;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) g2 += AN(j, i) * AN(l, i);
+                const bool al = (mask >> l) & 1u;
+                g2 = (aj && al) ? g2 : (j == l ? 1.0 : 0.0);
+                GM(j, l) = g2; GM(l, j) = g2;
+            }
+        }
+        double mind = INFINITY;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            double dj = GM(j, j);
+            const double diag = dj;
+#pragma unroll
+            for (int l = 0; l < j; ++l) dj -= L[j][l] * L[j][l];
+            mind = fmin(mind, dj / diag);
+            const double inv = rsqrt_f64(fmax(dj, 1e-300));
+            L[j][j] = inv;
+#pragma unroll
+            for (int i = j + 1; i < NV; ++i) {
+                double v = GM(i, j);
+#pragma unroll
+                for (int l = 0; l < j; ++l) v -= L[i][l] * L[j][l];
+                L[i][j] = v * inv;
+            }
+        }
+        if (!(mind > 1e-10)) { fail = true; break; }          // dependent guess
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            double v = ((mask >> j) & 1u) ? rhs[j] : 0.0;
+#pragma unroll
+            for (int l = 0; l < j; ++l) v -= L[j][l] * uu[l];
+            uu[j] = v * L[j][j];
+        }
+#pragma unroll
+        for (int j = NV - 1; j >= 0; --j) {
+            double v = uu[j];
+#pragma unroll
+            for (int l = j + 1; l < NV; ++l) v -= L[l][j] * uu[l];
+            uu[j] = v * L[j][j];
+        }
+        unsigned neg = 0;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) if (((mask >> j) & 1u) && !(uu[j] >= 0.0)) neg |= 1u << j;
+        if (neg == 0u) break;
+        if (round == NV) { fail = true; break; }
+        mask &= ~neg;                                           // drop the rows with negative multipliers
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            if ((neg >> j) & 1u) {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) AN(j, i) = 0.0;
+                RC(j) = -1.0;
+            }
+        }
+        if (mask == 0u) break;
+    }
+    if (fail || mask == 0u) {                                   // back to the cold start
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) { AN(j, i) = 0.0; GM(j, i) = (i == j) ? 1.0 : 0.0; }
+            RC(j) = -1.0;
+        }
+        return;
+    }
+    // accept: multipliers, active mask, w = g + N u  (GM already holds the Gram matrix of the accepted slots)
+    s.amask = mask;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) s.u[j] = ((mask >> j) & 1u) ? uu[j] : 0.0;
+#pragma unroll
+    for (int k = 1; k <= N; ++k) {
+        double ax = s.gx, ay = s.gy;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) { ax += s.u[j] * AN(j, 2 * (k - 1)); ay += s.u[j] * AN(j, 2 * (k - 1) + 1); }
+        s.px[k] = ax; s.py[k] = ay;
+    }
+}
+
+// Row codes of the final active set, shifted by one stage for the next MPC step (stage k of this step is stage k-1 of
+// the next one; rows of the first stage disappear).  out[j] = -1 where nothing carries over.
+template <int N, int MO, int WS>
+LDCBF_HD void shift_codes(const QpState<N, MO>& s, const double* ws, int (&out)[2 * N]) {
+    constexpr int NV = 2 * N;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        int code = ((s.amask >> j) & 1u) ? (int)RC(j) : -1;
+        if (code >= 0) {
+            const int id = code >> 1, side = code & 1;
+            int nid = -1;
+            if (id < 2 * N) nid = (id >= 2) ? id - 2 : -1;                           // leg(k) -> leg(k-1)
+            else if (id < 4 * N) nid = (id - 2 * N >= 2) ? id - 2 : -1;              // vel(k) -> vel(k-1)
+            else if (id < 4 * N + N * MO) nid = (id - 4 * N >= MO) ? id - MO : -1;   // cbf(k,o) -> cbf(k-1,o)
+            code = nid >= 0 ? 2 * nid + side : -1;
+        }
+        out[j] = code;
+    }
+}
+
 #undef AN
 #undef GM
+#undef RC
 
 // Outputs: states, footsteps, objective (NaN when not solved).
 template <int N, int MO>

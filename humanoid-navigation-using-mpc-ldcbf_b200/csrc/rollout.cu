@@ -21,6 +21,7 @@ struct RolloutIO {
     double* state; const double* goals; const int8_t* right_first; const double2* verts; const int32_t* nverts;
     const int32_t* nobs; const double* delta; const double* limits; double* traj_X; double* traj_U;
     int32_t* steps; int32_t* goal_steps; int32_t* status; unsigned long long* total_solves; bool fast_geometry;
+    bool warm_start;
 };
 
 template <int N, int MO, bool EXACT, int BLOCK>
@@ -40,6 +41,9 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
     if (tX) { tX[0] = px; tX[1] = vx; tX[2] = py; tX[3] = vy; tX[4] = th; }
 
     int gi = 0, kstep = 0, total = 0, solves = 0, last_status = LDCBF_STATUS_SOLVED;
+    int warm[2 * N];                       // active set of the previous step, shifted by one stage (-1: none)
+#pragma unroll
+    for (int j = 0; j < 2 * N; ++j) warm[j] = -1;
     double last_obj = INFINITY, ux = 0.0, uy = 0.0;
     for (int i = 0; i < n_goals; ++i) io.goal_steps[(size_t)b * n_goals + i] = 0;
 
@@ -47,6 +51,8 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
         if (last_obj < C.stop_objective || kstep >= max_steps_per_goal) {     // :392 / loop exhausted
             io.goal_steps[(size_t)b * n_goals + gi] = kstep;
             ++gi; kstep = 0; last_obj = INFINITY;
+#pragma unroll
+            for (int j = 0; j < 2 * N; ++j) warm[j] = -1;                      // a fresh run per sub-goal
             continue;
         }
         const double gx = io.goals[((size_t)b * n_goals + gi) * 2], gy = io.goals[((size_t)b * n_goals + gi) * 2 + 1];
@@ -67,13 +73,22 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
 #pragma unroll
             for (int k = 0; k <= N; ++k) ft[k] = (((step_number + k) & 1) == (right_first ? 0 : 1)) ? 1 : -1;
             QpSolution<N> S;
-            solve_scenario<N, MO, BLOCK>(C, px, vx, py, vy, th, gx, gy, ft, ce, nb, nullptr, 0, dl, lim,
-                                         qp_ws + threadIdx.x, S);
+            {
+                QpState<N, MO> qs;
+                double* ws = qp_ws + threadIdx.x;
+                qp_setup<N, MO, BLOCK>(C, px, vx, py, vy, th, gx, gy, ft, ce, nb, nullptr, 0, dl, lim, ws, qs);
+                if (io.warm_start) qp_warm_start<N, MO, BLOCK>(C, warm, ws, qs);
+                while (!qs.done) qp_trip<N, MO, BLOCK>(C, ws, qs);
+                qp_finish<N, MO>(C, qs, S);
+                shift_codes<N, MO, BLOCK>(qs, ws, warm);
+            }
             ++solves;
             last_status = S.status;
             if (S.status != LDCBF_STATUS_SOLVED) {                                    // :419-429 break
                 io.goal_steps[(size_t)b * n_goals + gi] = kstep;
                 ++gi; kstep = 0; last_obj = INFINITY;
+#pragma unroll
+                for (int j = 0; j < 2 * N; ++j) warm[j] = -1;
                 continue;
             }
             last_obj = S.obj;
@@ -161,7 +176,7 @@ extern "C" int ldcbf_rollout_f64(const ldcbf_params* prm, int B, int N, int T, i
     const RolloutIO io{state, goals, right_first, reinterpret_cast<const double2*>(verts), nverts, nobs, delta, limits,
                        traj_X, traj_U, steps, goal_steps, status,
                        reinterpret_cast<unsigned long long*>(total_solves),
-                       (prm->flags & LDCBF_FLAG_FAST_GEOMETRY) != 0};
+                       (prm->flags & LDCBF_FLAG_FAST_GEOMETRY) != 0, (prm->flags & LDCBF_FLAG_COLD_START) == 0};
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     switch (N) {
         case 1: return dispatch_rollout<1>(C, B, T, n_goals, max_steps_per_goal, sub, max_obs, max_verts, io, st);

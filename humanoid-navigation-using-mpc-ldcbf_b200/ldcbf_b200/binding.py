@@ -28,6 +28,7 @@ class LdcbfParams(ctypes.Structure):
 
 
 FLAG_FAST_GEOMETRY = 1
+FLAG_COLD_START = 2
 
 
 class Status:

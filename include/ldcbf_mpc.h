@@ -71,6 +71,9 @@ typedef struct ldcbf_params {
  * FAST_GEOMETRY trades that for ~1 ulp agreement (one reciprocal instead of two square roots and a division per
  * edge); use it only when bit parity of (c, eta) with the reference is not needed. */
 #define LDCBF_FLAG_FAST_GEOMETRY 1
+/* ldcbf_rollout_f64 warm-starts every solve from the previous step's active set shifted by one stage (the result is
+ * exact either way; the reference warm-starts IPOPT the same way, HumanoidMpc.py:450-455).  COLD_START disables it. */
+#define LDCBF_FLAG_COLD_START 2
 
 /* Optional per-scenario overrides of the limits `bounds_tuning.py:22-26` mutates:
  * limits[b] = (ALPHA, V_MAX[0], V_MAX[1], OMEGA_MAX, OMEGA_MIN, reserved).  NaN entries fall back to ldcbf_params. */

@@ -124,3 +124,48 @@ def test_host_build_with_streamed_obstacles(host_lib):
     ref = helpers.oracle_steps(states, goals, foots, [rings] * B, np.zeros(B))
     assert compare(out, ref) < 1e-6
     assert sum(r["status"] == 0 for r in ref) > 50
+
+
+def test_host_build_warm_start_is_exact_and_cheaper(host_lib):
+    """Closed loops with the warm start of the rollout kernel (previous active set shifted by one stage): every step
+    equals the oracle's optimum, and the active-set trips drop by more than half."""
+    import ldcbf_b200
+    from ldcbf_b200.binding import LdcbfParams
+    from ldcbf_b200 import scenarios
+    prm = LdcbfParams()
+    ldcbf_b200.lib().ldcbf_params_default(ctypes.byref(prm))
+    prm.sampling_time = 0.4
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    sc = scenarios.config2(12, seed=21)
+    cold_trips, warm_trips, steps = 0, 0, 0
+    for b in range(12):
+        state = sc["state"][b].copy()
+        s_v = model.foot_parity(400, bool(sc["right_first"][b]))
+        codes = np.full(6, -1, dtype=np.int32)
+        for k in range(60):
+            ce, nobs = c_eta_of(state[None, :], [sc["rings"][b]])
+            r = mpc.mpc_step(state, sc["goal"][b], sc["rings"][b], s_v[k:k + 4], sampling_time=0.4, delta=1e-6)
+            U, X = np.zeros((3, 2)), np.zeros((4, 4))
+            obj, st, it = np.zeros(1), np.zeros(1, np.int32), np.zeros(1, np.int32)
+            out_codes = np.zeros(6, dtype=np.int32)
+            x0, g = np.ascontiguousarray(state[:4]), np.ascontiguousarray(sc["goal"][b])
+            ft = np.array(s_v[k:k + 4], dtype=np.int8)
+            cee = np.ascontiguousarray(ce[0])
+            host_lib.qp_host_solve_n3_warm(ctypes.byref(prm), cee.shape[0], P(x0), ctypes.c_double(state[4]), P(g), P(ft), P(cee),
+                                           int(nobs[0]), ctypes.c_double(1e-6), P(codes), P(out_codes), P(U), P(X), P(obj), P(st), P(it))
+            cold = host_solve(host_lib, state[None, :], sc["goal"][b][None, :], ft[None, :], ce, nobs, np.array([1e-6]))
+            assert st[0] == r["status"] == cold["status"][0], (b, k)
+            if r["status"] != 0 or r["obj"] < 0.05:
+                break
+            # warm start, cold start and the oracle reach the same optimum.  Along directions in which the objective
+            # is flat to first order (few active rows) the three agree to ~1e-6 in U while their objectives agree to
+            # 1e-12: steps that add a nearly dependent row amplify rounding in w += t z.  Tolerance of the task: 1e-4.
+            assert np.abs(U - cold["U"][0]).max() < 1e-5 and np.abs(X - cold["X"][0]).max() < 1e-5, (b, k)
+            assert np.abs(U - r["U"]).max() < 1e-5 and np.abs(X - r["X"]).max() < 1e-5, (b, k, np.abs(U - r["U"]).max())
+            assert abs(obj[0] - r["obj"]) <= 1e-9 * r["obj"] and abs(obj[0] - cold["obj"][0]) <= 1e-9 * r["obj"]
+            cold_trips += int(cold["iters"][0]); warm_trips += int(it[0]); steps += 1
+            codes = out_codes
+            state = np.concatenate([X[1], [r["theta"][1]]])
+    assert steps > 200
+    print(f"trips per step: cold {cold_trips / steps:.2f}  warm {warm_trips / steps:.2f}")
+    assert warm_trips < 0.6 * cold_trips
