@@ -284,6 +284,7 @@ def run_ours(args):
             line["rollout"] = rollout_bench(L, sc, torch)
             line["rollout_margin_1e-6"] = rollout_bench(L, sc, torch, delta=1e-6)
             line["lidar"] = lidar_bench(L, flush, peak_fp64, torch)
+            line["subgoal_rollout"] = subgoal_rollout_bench(L, torch)
             line["unknown_env"] = unknown_env_bench(L, flush, torch)
             line["latency_b1"] = latency_b1(L, torch)
             line["bounds_tuning"] = bounds_tuning_bench(torch)
@@ -378,6 +379,38 @@ def rollout_bench(L, sc, torch, T=150, delta=None):
             "us_per_step_of_batch": 1e3 * ms / max(1, int(r["steps"].max().item())), "delta": delta or 0.0,
             "runs_ending_by_stop_rule": int((r["status"] == 0).sum().item()),
             "runs_ending_infeasible": int((r["status"] == 2).sum().item())}
+
+
+def subgoal_rollout_bench(L, torch, B=8192, per_goal=300):
+    """Config 4 (the per-GPU share of 65536 scenarios over 8 GPUs): sequential sub-goal runs around a wall, a fresh
+    run per way-point (HumanoidMPCWithRRT.py:153-181), all in one rollout launch."""
+    from ldcbf_b200 import scenarios
+    c4 = scenarios.config4(B, seed=0)
+    cu = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).cuda()
+    prm = L.default_params(0.4)
+    goals, v, nv, no = cu(c4["goals"]), cu(c4["verts"]), cu(c4["nverts"], torch.int32), cu(c4["nobs"], torch.int32)
+    rf = cu(c4["right_first"].astype(np.int8), torch.int8)
+    delta = torch.full((B,), 1e-6, dtype=torch.float64, device="cuda")
+    G = goals.shape[1]
+    run = lambda: L.rollout(prm, cu(c4["state"]), goals, rf, v, nv, no, T=G * 120, N=N_HORIZON,
+                            max_steps_per_goal=per_goal, delta=delta, record=False)
+    for _ in range(2):
+        r = run()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = run()
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = statistics.median(ts)
+    solves = int(r["total_solves"].item())
+    gs = r["goal_steps"]
+    return {"batch": B, "sub_goals": G, "solves": solves, "ms": ms, "value": solves / (ms * 1e-3), "unit": UNIT,
+            "scenarios_reaching_last_goal": int((gs[:, -1] > 0).sum().item()),
+            "mean_steps_per_scenario": float(r["steps"].double().mean().item())}
 
 
 def lidar_bench(L, flush, peak_fp64, torch, B=16384):

@@ -132,3 +132,24 @@ def config3(B=16384, seed=0, pool=64, n_obstacles=20):
     state[:, 0], state[:, 2], state[:, 4] = pos[:, 0], pos[:, 1], math.pi / 2
     return dict(state=state, goal=np.tile([4.0, 3.5], (B, 1)), verts=verts_p[idx], nverts=nverts_p[idx], nobs=nobs_p[idx],
                 rings=maps, map_index=idx, pos=pos)
+
+
+def config4(B=8192, seed=0, n_goals=6):
+    """RRT* sub-goal variant (`report_simulations/simulation_rrt.py:18-24`): one wall
+    `ConvexHull([[2,-3],[2,3],[3,-3],[3,3]])`, start at the origin, goal (5, 0).  RRT* planning is out of scope, so the
+    way-points are an input: `n_goals` points routed around either end of the wall with U(-0.3, 0.3) jitter, the last
+    one the goal itself.  Returns dict(state[B,5], goals[B,n_goals,2], verts[B,1,4,2], nverts, nobs, right_first)."""
+    rng = np.random.default_rng(seed)
+    wall = np.array([[2.0, -3.0], [3.0, -3.0], [3.0, 3.0], [2.0, 3.0]])          # hull vertices, counter-clockwise
+    side = np.where(rng.random(B) < 0.5, 1.0, -1.0)                               # pass above (+) or below (-) the wall
+    base = np.array([[1.0, 1.5], [1.6, 3.0], [2.5, 3.9], [3.6, 3.0], [4.4, 1.5], [5.0, 0.0]])
+    if n_goals != len(base):
+        t = np.linspace(0, len(base) - 1, n_goals)
+        base = np.column_stack([np.interp(t, np.arange(len(base)), base[:, i]) for i in range(2)])
+    goals = np.tile(base, (B, 1, 1))
+    goals[:, :, 1] *= side[:, None]
+    goals[:, :-1] += rng.uniform(-0.3, 0.3, (B, n_goals - 1, 2))
+    goals[:, -1] = (5.0, 0.0)
+    verts, nverts, nobs = pack_rings([[wall]] * B, 1, 4)
+    return dict(state=np.zeros((B, 5)), goals=goals, verts=verts, nverts=nverts, nobs=nobs,
+                right_first=np.ones(B, dtype=bool), rings=[wall])

@@ -107,3 +107,32 @@ def test_scenario_generator_and_foot_window():
         assert ring.shape == ref.shape
         j = int(np.argmin(np.abs(ref - ring[0]).sum(1)))
         np.testing.assert_allclose(np.roll(ref, -j, axis=0), ring, atol=1e-15)
+
+
+def test_crowded_map_reproduced():
+    """f4: the mirror's seeded generators rebuild the reference's CROWDED map (seed 10, simulation_1.py:201-218) and
+    its fixed maps bit for bit; the goldens were produced by the reference's own Scenario.load_scenario."""
+    pytest.importorskip("torch")
+    import importlib
+    import torch
+    if not torch.cuda.is_available():
+        # the mirror package imports ldcbf_b200 (loads the .so, no device needed) — fine on CPU
+        pass
+    from HumanoidNavigation.report_simulations.Scenario import Scenario
+    from HumanoidNavigation.Utils.ObstaclesUtils import ObstaclesUtils
+    from HumanoidNavigation.Utils.obstacles import set_seed
+    g = np.load(os.path.join(ROOT, "tests", "golden", "geometry_golden.npz"))
+    ObstaclesUtils.set_random_seed(10)
+    set_seed(10)
+    _, _, obs = Scenario.load_scenario(Scenario.CROWDED, (0, 0), (4, 3.5), 20, range_x=(-1, 6), range_y=(-1, 6))
+    assert len(obs) == int(g["crowded10/n_obs"]) == 20
+    for o, h in enumerate(obs):
+        assert np.array_equal(h.points, g[f"crowded10/obs{o}/points"])
+        assert np.array_equal(h.vertices, g[f"crowded10/obs{o}/vertices"])
+    for name, key in (("MAIN_PAPER", "main_paper"), ("CIRCLE_OBSTACLES", "circles")):
+        _, _, obs = Scenario.load_scenario(getattr(Scenario, name), (0, 3), (6, -3))
+        assert len(obs) == int(g[f"{key}/n_obs"])
+        for o, h in enumerate(obs):
+            assert np.array_equal(h.points, g[f"{key}/obs{o}/points"])
+    _, _, maze = Scenario.load_scenario(Scenario.MAZE_1, None, None)
+    assert len(maze) == 8
