@@ -20,15 +20,16 @@ struct StepIO {
     const double* x0; const double* theta0; const double* goal; const int8_t* foot;
     const double* c_eta; const int32_t* nobs; const double* delta; const double* limits;
     double* U; double* X; double* theta; double* omega; double* obj; int32_t* status; int32_t* iters;
-    // loop-shaped variant (ldcbf_mpc_step_packed_f64): state rows [B,5] in (x0/theta0 unused), next rows [B,8] out
-    const double* state5; double* next8;
+    // loop-shaped variant (ldcbf_mpc_step_packed_f64): state rows [B,6] in (x0/theta0/foot unused), next rows [B,10] out
+    const double* state6; double* next10;
 };
 
 __device__ __forceinline__ void load_state(const StepIO& io, int b, double4& x, double& th) {
-    if (io.state5) {
-        const double* s = io.state5 + 5 * (size_t)b;
-        x = make_double4(s[0], s[1], s[2], s[3]);
-        th = s[4];
+    if (io.state6) {
+        const double2* s = reinterpret_cast<const double2*>(io.state6) + 3 * (size_t)b;
+        const double2 a = s[0], c = s[1], e = s[2];
+        x = make_double4(a.x, a.y, c.x, c.y);
+        th = e.x;
     } else {
         x = reinterpret_cast<const double4*>(io.x0)[b];          // (p_x, v_x, p_y, v_y)
         th = io.theta0[b];
@@ -37,10 +38,13 @@ __device__ __forceinline__ void load_state(const StepIO& io, int b, double4& x, 
 
 template <int N>
 __device__ __forceinline__ void store_solution(const QpSolution<N>& S, int b, const StepIO& io) {
-    if (io.next8) {     // (x_next[4], theta_1, u0_x, u0_y, omega_0)
-        double4* o = reinterpret_cast<double4*>(io.next8) + 2 * (size_t)b;
-        o[0] = make_double4(S.px[1], S.vx[1], S.py[1], S.vy[1]);
-        o[1] = make_double4(S.th[1], S.ux[0], S.uy[0], S.om[0]);
+    if (io.next10) {    // (x_next[4], theta_1, u0_x, u0_y, omega_0, objective, status)
+        double2* o = reinterpret_cast<double2*>(io.next10) + 5 * (size_t)b;
+        o[0] = make_double2(S.px[1], S.vx[1]);
+        o[1] = make_double2(S.py[1], S.vy[1]);
+        o[2] = make_double2(S.th[1], S.ux[0]);
+        o[3] = make_double2(S.uy[0], S.om[0]);
+        o[4] = make_double2(S.obj, (double)S.status);
     }
     if (io.U) {
         double2* U2 = reinterpret_cast<double2*>(io.U) + (size_t)b * N;
@@ -54,9 +58,23 @@ __device__ __forceinline__ void store_solution(const QpSolution<N>& S, int b, co
 #pragma unroll
         for (int k = 0; k < N; ++k) io.omega[(size_t)b * N + k] = S.om[k];
     }
-    io.obj[b] = S.obj;
-    io.status[b] = S.status;
-    io.iters[b] = S.iters;
+    if (io.obj) io.obj[b] = S.obj;
+    if (io.status) io.status[b] = S.status;
+    if (io.iters) io.iters[b] = S.iters;
+}
+
+// Foot-parity window: read from the foot array, or derived from the first stance foot of the packed state row
+// (the reference's s_v alternates strictly, HumanoidMpc.py:104-108, so foot[j] = foot[0] * (-1)^j).
+template <int N>
+__device__ __forceinline__ void load_foot(const StepIO& io, int b, int (&ft)[N + 1]) {
+    if (io.state6) {
+        const int f0 = io.state6[6 * (size_t)b + 5] < 0.0 ? -1 : 1;
+#pragma unroll
+        for (int k = 0; k <= N; ++k) ft[k] = (k & 1) ? -f0 : f0;
+    } else {
+#pragma unroll
+        for (int k = 0; k <= N; ++k) ft[k] = io.foot[(size_t)b * (N + 1) + k];
+    }
 }
 
 // One thread per scenario; BLOCK threads per block (32 for small batches so the warps spread over all SMs, 128
@@ -71,8 +89,7 @@ __global__ void __launch_bounds__(BLOCK) mpc_qp_kernel(StepConst C, int B, int m
     load_state(io, b, x, th0);
     const double2 g = reinterpret_cast<const double2*>(io.goal)[b];
     int ft[N + 1];
-#pragma unroll
-    for (int k = 0; k <= N; ++k) ft[k] = io.foot[(size_t)b * (N + 1) + k];
+    load_foot<N>(io, b, ft);
     const Limits lim = load_limits(C, io.limits, (size_t)b);
     const int nt = min(io.nobs[b], max_obs);
     const int nb = min(nt, MO);
@@ -129,8 +146,7 @@ __global__ void __launch_bounds__(BLOCK) mpc_qp_refill_kernel(StepConst C, int B
                     load_state(io, b, x, th0);
                     const double2 g = reinterpret_cast<const double2*>(io.goal)[b];
                     int ft[N + 1];
-#pragma unroll
-                    for (int k = 0; k <= N; ++k) ft[k] = io.foot[(size_t)b * (N + 1) + k];
+                    load_foot<N>(io, b, ft);
                     const Limits lim = load_limits(C, io.limits, (size_t)b);
                     const int nt = min(io.nobs[b], max_obs);
                     const int nb = min(nt, MO);
@@ -242,19 +258,18 @@ extern "C" int ldcbf_mpc_qp_f64(const ldcbf_params* prm, int B, int N, int max_o
 }
 
 extern "C" int ldcbf_mpc_step_packed_f64(const ldcbf_params* prm, int B, int N, int max_obs, int max_verts,
-                                         const double* state, const double* goal, const int8_t* foot,
-                                         const double* verts, const int32_t* nverts, const int32_t* nobs,
-                                         const double* delta, const double* limits, double* next, double* c_eta,
-                                         double* obj, int32_t* status, int32_t* iters, void* cuda_stream) {
+                                         const double* state, const double* goal, const double* verts,
+                                         const int32_t* nverts, const int32_t* nobs, const double* delta,
+                                         const double* limits, double* next, double* c_eta, int32_t* iters,
+                                         void* cuda_stream) {
     if (!prm || B < 0 || max_obs <= 0 || max_verts <= 0) return LDCBF_E_ARG;
     if (B == 0) return LDCBF_OK;
-    if (!state || !goal || !foot || !verts || !nverts || !nobs || !next || !c_eta || !obj || !status || !iters)
-        return LDCBF_E_ARG;
-    int rc = launch_halfplanes(B, max_obs, max_verts, state, 5, 2, verts, nverts, nobs, c_eta,
+    if (!state || !goal || !verts || !nverts || !nobs || !next || !c_eta) return LDCBF_E_ARG;
+    int rc = launch_halfplanes(B, max_obs, max_verts, state, 6, 2, verts, nverts, nobs, c_eta,
                                (prm->flags & LDCBF_FLAG_FAST_GEOMETRY) != 0, cuda_stream);
     if (rc != LDCBF_OK) return rc;
-    const StepIO io{nullptr, nullptr, goal, foot, c_eta, nobs, delta, limits, nullptr, nullptr, nullptr, nullptr,
-                    obj, status, iters, state, next};
+    const StepIO io{nullptr, nullptr, goal, nullptr, c_eta, nobs, delta, limits, nullptr, nullptr, nullptr, nullptr,
+                    nullptr, nullptr, iters, state, next};
     return dispatch_horizon(*prm, B, N, max_obs, io, cuda_stream);
 }
 

@@ -50,37 +50,30 @@ class BatchedHumanoidMPC:
         return self._out
 
     # ---- end-to-end step: host buffers in, host buffers out -----------------------------------------------
-    def step_host(self, state_host, foot_host):
-        """state_host: pinned [B,5] fp64 tensor (p_x, v_x, p_y, v_y, theta); foot_host: pinned [B,N+1] int8.
-        Copies the inputs host->device, runs the loop-shaped step (`ldcbf_mpc_step_packed_f64`), copies
-        next[B,8] = (x_next[4], theta_1, u0_x, u0_y, omega_0), obj and status back into pinned host buffers and
-        synchronises.  Returns the dict of pinned host tensors (reused between calls)."""
-        B, N = self.B, self.N
+    def step_host(self, state_host):
+        """state_host: pinned [B,6] fp64 tensor (p_x, v_x, p_y, v_y, theta, first stance foot +-1).
+        One upload, the loop-shaped step (`ldcbf_mpc_step_packed_f64`), one download and a stream synchronise.
+        Returns the pinned host tensor next[B,10] = (x_next[4], theta_1, u0_x, u0_y, omega_0, objective, status),
+        reused between calls."""
+        B = self.B
         if self._pinned is None:
-            pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
-            self._pinned = dict(next=pin((B, 8), torch.float64), obj=pin((B,), torch.float64),
-                                status=pin((B,), torch.int32))
-            self._d_state = torch.empty((B, 5), dtype=torch.float64, device=self.device)
-            self._d_foot = torch.empty((B, N + 1), dtype=torch.int8, device=self.device)
+            self._pinned = torch.empty((B, 10), dtype=torch.float64).pin_memory()
+            self._d_state = torch.empty((B, 6), dtype=torch.float64, device=self.device)
             self._packed = None
         self._d_state.copy_(state_host, non_blocking=True)
-        self._d_foot.copy_(foot_host, non_blocking=True)
-        o = self._packed = _b.mpc_step_packed(self.prm, self._d_state, self.goal, self._d_foot, self.verts, self.nverts,
-                                              self.nobs, delta=self.delta, limits=self.limits, out=self._packed)
-        p = self._pinned
-        p["next"].copy_(o["next"], non_blocking=True)
-        p["obj"].copy_(o["obj"], non_blocking=True)
-        p["status"].copy_(o["status"], non_blocking=True)
+        o = self._packed = _b.mpc_step_packed(self.prm, self._d_state, self.goal, self.verts, self.nverts, self.nobs,
+                                              N=self.N, delta=self.delta, limits=self.limits, out=self._packed)
+        self._pinned.copy_(o["next"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return p
+        return self._pinned
 
     @property
     def h2d_bytes_per_step(self):
-        return self.B * (5 * 8 + (self.N + 1))
+        return self.B * 6 * 8
 
     @property
     def d2h_bytes_per_step(self):
-        return self.B * (8 * 8 + 8 + 4)
+        return self.B * 10 * 8
 
     # ---- closed loop -----------------------------------------------------------------------------------------
     def rollout(self, state, right_first, T, goals=None, max_steps_per_goal=None, record=True):

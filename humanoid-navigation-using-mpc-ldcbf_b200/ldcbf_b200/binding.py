@@ -56,7 +56,7 @@ def lib():
         L.ldcbf_halfplanes_f64.argtypes = [c_int, c_int, c_int, P, P, P, P, P, P]
         L.ldcbf_mpc_qp_f64.argtypes = [POINTER(LdcbfParams), c_int, c_int, c_int] + [P] * 16
         L.ldcbf_mpc_step_f64.argtypes = [POINTER(LdcbfParams), c_int, c_int, c_int, c_int] + [P] * 19
-        L.ldcbf_mpc_step_packed_f64.argtypes = [POINTER(LdcbfParams), c_int, c_int, c_int, c_int] + [P] * 14
+        L.ldcbf_mpc_step_packed_f64.argtypes = [POINTER(LdcbfParams), c_int, c_int, c_int, c_int] + [P] * 11
         L.ldcbf_lidar_cast_f64.argtypes = [c_int, c_int, P, c_double, P, c_int, c_int, P, P, P, P, P, P, P]
         L.ldcbf_lidar_clusters_f64.argtypes = [c_int, c_int, P, P, c_double, c_int, c_int, c_int, P, P, P, P, P, P]
         L.ldcbf_rollout_f64.argtypes = [POINTER(LdcbfParams)] + [c_int] * 7 + [P] * 15
@@ -179,23 +179,21 @@ def mpc_step(prm, x0, theta0, goal, foot, verts, nverts, nobs, delta=None, warm=
     return out
 
 
-def mpc_step_packed(prm, state, goal, foot, verts, nverts, nobs, delta=None, limits=None, out=None):
-    """Loop-shaped step: state[B,5] in -> dict(next[B,8] = (x_next[4], theta_1, u0_x, u0_y, omega_0), c_eta, obj,
-    status, iters)."""
-    B, N = state.shape[0], foot.shape[1] - 1
+def mpc_step_packed(prm, state, goal, verts, nverts, nobs, N=3, delta=None, limits=None, out=None):
+    """Loop-shaped step: state[B,6] = (p_x, v_x, p_y, v_y, theta, first stance foot +-1) in ->
+    dict(next[B,10] = (x_next[4], theta_1, u0_x, u0_y, omega_0, objective, status), c_eta, iters)."""
+    B = state.shape[0]
     max_obs, max_verts = verts.shape[1], verts.shape[2]
     out = {} if out is None else out
     dev = state.device
-    for name, shape, dt in (("next", (B, 8), F64), ("c_eta", (B, max_obs, 4), F64), ("obj", (B,), F64),
-                            ("status", (B,), I32), ("iters", (B,), I32)):
+    for name, shape, dt in (("next", (B, 10), F64), ("c_eta", (B, max_obs, 4), F64), ("iters", (B,), I32)):
         if out.get(name) is None:
             out[name] = torch.empty(shape, dtype=dt, device=dev)
-    _check(lib().ldcbf_mpc_step_packed_f64(ctypes.byref(prm), B, N, max_obs, max_verts, _ptr(state, F64, "state"),
-                                           _ptr(goal, F64, "goal"), _ptr(foot, I8, "foot"), _ptr(verts, F64, "verts"),
+    _check(lib().ldcbf_mpc_step_packed_f64(ctypes.byref(prm), B, int(N), max_obs, max_verts, _ptr(state, F64, "state"),
+                                           _ptr(goal, F64, "goal"), _ptr(verts, F64, "verts"),
                                            _ptr(nverts, I32, "nverts"), _ptr(nobs, I32, "nobs"),
                                            _ptr(delta, F64, "delta"), _ptr(limits, F64, "limits"),
                                            _ptr(out["next"], F64, "next"), _ptr(out["c_eta"], F64, "c_eta"),
-                                           _ptr(out["obj"], F64, "obj"), _ptr(out["status"], I32, "status"),
                                            _ptr(out["iters"], I32, "iters"), _stream()), "ldcbf_mpc_step_packed_f64")
     return out
 

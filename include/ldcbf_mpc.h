@@ -120,14 +120,16 @@ int ldcbf_mpc_step_f64(const ldcbf_params* prm, int B, int N, int max_obs, int m
                        double* obj, int32_t* status, int32_t* iters, void* cuda_stream);
 
 /* Loop-shaped variant of ldcbf_mpc_step_f64 for closed loops driven from the host (the reference's
- * run_simulation keeps its state in X_pred[:, k], HumanoidMpc.py:396-447): state rows in, next rows out, so one step
- * costs two uploads and three downloads.
- *   state [B,5] (p_x, v_x, p_y, v_y, theta)
- *   next  [B,8] out = (x_next[4], theta_1, u0_x, u0_y, omega_0);  c_eta [B,max_obs,4] scratch / out */
+ * run_simulation keeps its state in X_pred[:, k], HumanoidMpc.py:396-447): ONE row in and ONE row out per scenario, so
+ * a step costs one upload and one download.
+ *   state [B,6] (p_x, v_x, p_y, v_y, theta, first stance foot +1/-1); the foot window alternates from the first
+ *               foot exactly like the reference's s_v list (HumanoidMpc.py:104-108, :403)
+ *   next  [B,10] out = (x_next[4], theta_1, u0_x, u0_y, omega_0, objective, status as a double)
+ *   c_eta [B,max_obs,4] scratch / out;  iters [B] out or NULL */
 int ldcbf_mpc_step_packed_f64(const ldcbf_params* prm, int B, int N, int max_obs, int max_verts, const double* state,
-                              const double* goal, const int8_t* foot, const double* verts, const int32_t* nverts,
-                              const int32_t* nobs, const double* delta, const double* limits, double* next,
-                              double* c_eta, double* obj, int32_t* status, int32_t* iters, void* cuda_stream);
+                              const double* goal, const double* verts, const int32_t* nverts, const int32_t* nobs,
+                              const double* delta, const double* limits, double* next, double* c_eta,
+                              int32_t* iters, void* cuda_stream);
 
 /* K4 — LiDAR ray casting.  Replaces compute_lidar_readings / get_closest_point
  * (RangeFinder/range_finder_wth_polygons_dbscan.py:13-63) and line_polygon_intersection (Utils/obstacles.py:95-139).

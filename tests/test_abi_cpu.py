@@ -61,6 +61,7 @@ def test_argument_errors_without_device(lib):
     assert lib.ldcbf_mpc_qp_f64(ctypes.byref(p), 2, 3, 3, *([None] * 16)) == -1
     assert lib.ldcbf_mpc_qp_f64(None, 2, 3, 3, *([None] * 16)) == -1
     assert lib.ldcbf_mpc_step_f64(ctypes.byref(p), 0, 3, 3, 24, *([None] * 19)) == 0
+    assert lib.ldcbf_mpc_step_packed_f64(ctypes.byref(p), 4, 3, 3, 24, *([None] * 11)) == -1
     assert lib.ldcbf_lidar_cast_f64(1, 0, None, 1.5, None, 3, 24, None, None, None, None, None, None, None) == -1
     assert lib.ldcbf_rollout_f64(ctypes.byref(p), 1, 3, 0, 1, 10, 3, 24, *([None] * 15)) == -1
     assert lib.ldcbf_workspace_bytes(4096, 3, 3, 24) == 0

@@ -212,24 +212,29 @@ def test_twenty_obstacle_known_map(L):
 
 
 def test_packed_step_and_host_path_equal_the_plain_step(L):
-    """ldcbf_mpc_step_packed_f64 (state rows in, next rows out) and BatchedHumanoidMPC.step_host give the same numbers."""
+    """ldcbf_mpc_step_packed_f64 (one state row in, one result row out) and BatchedHumanoidMPC.step_host give the same
+    numbers as the plain step."""
     from ldcbf_b200 import scenarios
     sc = scenarios.config2(300, seed=13)
     foots = scenarios.foot_window(sc["right_first"], 0, 3)
     verts, nverts, nobs = cu(sc["verts"]), cu(sc["nverts"], torch.int32), cu(sc["nobs"], torch.int32)
     prm = L.default_params(0.4)
     a = L.mpc_step(prm, cu(sc["state"][:, :4]), cu(sc["state"][:, 4]), cu(sc["goal"]), cu(foots, torch.int8), verts, nverts, nobs)
-    b = L.mpc_step_packed(prm, cu(sc["state"]), cu(sc["goal"]), cu(foots, torch.int8), verts, nverts, nobs)
+    state6 = np.column_stack((sc["state"], foots[:, 0].astype(np.float64)))
+    b = L.mpc_step_packed(prm, cu(state6), cu(sc["goal"]), verts, nverts, nobs)
     nxt = b["next"].cpu().numpy()
-    ok = a["status"].cpu().numpy() == 0
-    assert np.array_equal(a["status"].cpu().numpy(), b["status"].cpu().numpy())
+    st = a["status"].cpu().numpy()
+    ok = st == 0
+    assert np.array_equal(nxt[:, 9].astype(np.int32), st)
     assert np.array_equal(nxt[ok, :4], a["X"][:, 1].cpu().numpy()[ok])
     assert np.array_equal(nxt[ok, 4], a["theta"][:, 1].cpu().numpy()[ok])
     assert np.array_equal(nxt[ok, 5:7], a["U"][:, 0].cpu().numpy()[ok])
     assert np.array_equal(nxt[ok, 7], a["omega"][:, 0].cpu().numpy()[ok])
+    assert np.array_equal(nxt[ok, 8], a["obj"].cpu().numpy()[ok])
+    assert np.array_equal(b["iters"].cpu().numpy(), a["iters"].cpu().numpy())
     eng = L.BatchedHumanoidMPC(sc["goal"], sc["verts"], sc["nverts"], sc["nobs"], N_horizon=3, sampling_time=0.4)
-    h = eng.step_host(torch.as_tensor(sc["state"]).pin_memory(), torch.as_tensor(foots).pin_memory())
-    assert np.array_equal(h["next"].numpy()[ok], nxt[ok]) and np.array_equal(h["status"].numpy(), b["status"].cpu().numpy())
+    h = eng.step_host(torch.as_tensor(state6).pin_memory()).numpy()
+    assert np.array_equal(h[ok], nxt[ok]) and np.array_equal(h[:, 9], nxt[:, 9])
 
 
 def test_infeasible_and_degenerate_status(L):

@@ -7,7 +7,9 @@ from ldcbf_b200.binding import FLAG_FAST_GEOMETRY
 sc = scenarios.config2(4096, seed=0)
 B = 1 << 20; rep = B // 4096
 cu = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(np.tile(a, (rep,) + (1,) * (a.ndim - 1))), dtype=dt).cuda()
-st = cu(sc["state"]); g = cu(sc["goal"]); ft = cu(scenarios.foot_window(sc["right_first"], 0, 3), torch.int8)
+import numpy as np
+fw = scenarios.foot_window(sc["right_first"], 0, 3)
+st = cu(np.column_stack((sc["state"], fw[:, 0].astype(np.float64)))); g = cu(sc["goal"])
 pos = cu(sc["state"][:, [0, 2]]); v, nv, no = cu(sc["verts"]), cu(sc["nverts"], torch.int32), cu(sc["nobs"], torch.int32)
 ce = torch.empty((B, 3, 4), dtype=torch.float64, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -23,5 +25,5 @@ print(f"K1 exact B={B}: {ms*1e3:.1f} us  {984*B/ms/1e6:.0f} GB/s")
 out = {}
 for flags, name in ((0, "exact"), (FLAG_FAST_GEOMETRY, "fast")):
     prm = L.default_params(0.4, flags=flags)
-    ms2 = timeit(lambda: L.mpc_step_packed(prm, st, g, ft, v, nv, no, out=out))
+    ms2 = timeit(lambda: L.mpc_step_packed(prm, st, g, v, nv, no, out=out))
     print(f"packed step ({name} geometry): {ms2*1e3:.1f} us  {B/ms2*1e3:.3e} solves/s")
