@@ -1,0 +1,469 @@
+// K2+K3 for long horizons (LDCBF_MAX_HORIZON < N <= LDCBF_MAX_HORIZON_LONG): one thread block per scenario.
+//
+// Same problem and same method as mpc_qp.cuh (heading schedule, rows and cost of HumanoidMpc.py:137-333 written in
+// the CoM positions w = (p_1..p_N), Goldfarb-Idnani dual active set), but with up to 2N = 96 unknowns, 4N + N*n_obs
+// rows and active sets of up to 2N rows the per-thread register formulation no longer fits, and the Gram/Cholesky
+// factor of the active normals loses the degenerate vertices long horizons produce (leg row k, velocity rows k and
+// k+1 are dependent to within the heading increment).  Here the block keeps an orthogonal factorisation of the
+// active normals in shared memory, N_A = Q [R; 0] with Q = J (n x n) and R upper triangular:
+//     d = J^T n+,   r = R^-1 d[0:q)  (dual step),   z = J[:, q:) d[q:)  (primal step),   |z|^2 = z.n+ = |d[q:)|^2
+//     add a row:    one Householder reflection on the free columns of J, new column (d[0:q), -+|d[q:)|) of R
+//     drop a row:   delete the column of R, restore the triangle with Givens rotations, same rotations on J
+// which is backward stable: the 150-instance sweeps of tools/proto_long_horizon.py (N = 20, 40) match the
+// Lawson-Hanson oracle (oracle/qp_pspace.py) to 1e-7.
+//
+// Work split inside a block (T threads): matrix-vector products by thread-per-column / thread-per-row over the padded
+// (odd leading dimension: conflict-free both ways) shared arrays, the violation scan by thread-per-row with a block
+// arg-min, the triangular solve by warp 0 (column sweep, one shuffle per column) while the other warps form z.
+#include <limits.h>
+
+#include "mpc_qp.cuh"
+#include "step_io.cuh"
+
+namespace ldcbf {
+
+// R is stored packed: row i keeps the columns c >= i-1 (the triangle plus the one sub-diagonal that exists while a
+// column is being deleted); element (i, c) lives at R[long_rbase(i, n) + c].
+__host__ __device__ __forceinline__ int long_rbase(int i, int n) {
+    return i == 0 ? 0 : n + (i - 1) * (n + 1) - ((i - 1) * i) / 2 - (i - 1);
+}
+__host__ __device__ __forceinline__ int long_rsize(int n) { return n + (n - 1) * (n + 1) - ((n - 1) * n) / 2; }
+
+struct LongShared {
+    double *J, *R, *d, *r, *z, *u, *cs, *sn, *rdi;      // factorisation and step vectors
+    double *P, *V;                                       // iterate p_0..p_N (x, y interleaved) and velocities
+    double *th, *rc, *rs, *om, *vmid, *vhalf, *vinrm;    // heading schedule, merged longitudinal bounds, 1/|row|
+    double *ex, *ey, *hb, *eni;                          // half-planes: eta . p >= hb, 1/|eta|
+    double *redv;
+    int *ft, *acode, *redi;
+    unsigned char* act;                                  // row id -> currently in the active set
+};
+
+__host__ __device__ inline size_t long_carve(int N, int max_obs, char* base, LongShared* S) {
+    const int n = 2 * N, ld = n | 1;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* p = base + off; off += (bytes + 15) & ~size_t(15); return p; };
+    double* J = (double*)take(sizeof(double) * n * ld);
+    double* R = (double*)take(sizeof(double) * long_rsize(n));
+    double* vec = (double*)take(sizeof(double) * 7 * n);
+    double* P = (double*)take(sizeof(double) * 4 * (N + 1));
+    double* hs = (double*)take(sizeof(double) * 7 * (N + 1));
+    double* ob = (double*)take(sizeof(double) * 4 * max_obs);
+    double* redv = (double*)take(sizeof(double) * 32);
+    int* ints = (int*)take(sizeof(int) * (N + 1 + n + 32));
+    unsigned char* act = (unsigned char*)take((size_t)4 * N + (size_t)N * max_obs);
+    if (S) {
+        S->J = J; S->R = R;
+        S->d = vec; S->r = vec + n; S->z = vec + 2 * n; S->u = vec + 3 * n; S->cs = vec + 4 * n; S->sn = vec + 5 * n;
+        S->rdi = vec + 6 * n;
+        S->P = P; S->V = P + 2 * (N + 1);
+        S->th = hs; S->rc = hs + (N + 1); S->rs = hs + 2 * (N + 1); S->om = hs + 3 * (N + 1);
+        S->vmid = hs + 4 * (N + 1); S->vhalf = hs + 5 * (N + 1); S->vinrm = hs + 6 * (N + 1);
+        S->ex = ob; S->ey = ob + max_obs; S->hb = ob + 2 * max_obs; S->eni = ob + 3 * max_obs;
+        S->redv = redv;
+        S->ft = ints; S->acode = ints + (N + 1); S->redi = ints + (N + 1 + n);
+        S->act = act;
+    }
+    return off;
+}
+
+struct LongScalars {
+    double p0x, p0y, v0x, v0y, gx, gy, delta, vlat_mid, vlat_half;
+    double rx, ry, nn, s_p, u_p, t, d2n2, ab[2][2];
+    int q, status, iters, done, typ, k, code, full, dep, l, inner_done;
+};
+
+// Slack (natural units), deviation sign and 1/|normal| of row `row` at the current iterate.
+__device__ __forceinline__ void long_eval_row(int row, int N, int nobs, const LongShared& S, const StepConst& C,
+                                              const LongScalars& sc, double& slack, double& m, double& inrm) {
+    if (row < 2 * N) {
+        const int k = row >> 1;
+        const double dx = S.P[2 * (k + 1)] - S.P[2 * k], dy = S.P[2 * (k + 1) + 1] - S.P[2 * k + 1];
+        const double c = S.rc[k], s = S.rs[k];
+        if ((row & 1) == 0) { m = (c * dx + s * dy) - C.legx_mid; slack = C.legx_half - fabs(m); }
+        else { m = (c * dy - s * dx) - (C.legy_mid - (double)S.ft[k] * C.foot_offset); slack = C.legy_half - fabs(m); }
+        inrm = k == 0 ? 1.0 : 0.70710678118654752;
+    } else if (row < 4 * N) {
+        const int kk = ((row - 2 * N) >> 1) + 1;
+        const double Vx = S.V[2 * kk], Vy = S.V[2 * kk + 1];
+        const double c = S.rc[kk], s = S.rs[kk];
+        if ((row & 1) == 0) { m = (c * Vx + s * Vy) - S.vmid[kk]; slack = S.vhalf[kk] - fabs(m); }
+        else { m = ((double)S.ft[kk] * c * Vy - s * Vx) - sc.vlat_mid; slack = sc.vlat_half - fabs(m); }
+        inrm = S.vinrm[kk];
+    } else {
+        const int j = row - 4 * N;
+        const int kk = j / nobs + 1, o = j - (kk - 1) * nobs;
+        slack = S.ex[o] * S.P[2 * kk] + S.ey[o] * S.P[2 * kk + 1] - S.hb[o];
+        m = -1.0;
+        inrm = S.eni[o];
+    }
+}
+
+template <int T>
+__global__ void __launch_bounds__(T) mpc_long_kernel(StepConst C, int B, int N, int max_obs, int iter_cap, StepIO io) {
+    extern __shared__ __align__(16) char long_smem[];
+    __shared__ LongScalars sc;
+    LongShared S;
+    long_carve(N, max_obs, long_smem, &S);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = 2 * N, ld = n | 1;
+    const double nan = quiet_nan();
+
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        __syncthreads();
+        const int nobs = min(io.nobs[b], max_obs);
+        const int nrows = 4 * N + N * nobs;
+        // ------------------------------------------------------------------ setup
+        if (tid == 0) {
+            double4 x;
+            double th0;
+            load_state(io, b, x, th0);
+            const double2 g = reinterpret_cast<const double2*>(io.goal)[b];
+            const Limits lim = load_limits(C, io.limits, (size_t)b);
+            sc.p0x = x.x; sc.v0x = x.y; sc.p0y = x.z; sc.v0y = x.w; sc.gx = g.x; sc.gy = g.y;
+            sc.delta = io.delta ? io.delta[b] : 0.0;
+            sc.vlat_mid = 0.5 * (lim.vmax1 + C.v_min1); sc.vlat_half = 0.5 * (lim.vmax1 - C.v_min1);
+            const double phi = atan2(g.y - x.z, g.x - x.x);            // HumanoidMpc.py:137-160
+            double thk = th0;
+            S.th[0] = thk; S.vmid[0] = 0.0; S.vhalf[0] = 0.0; S.vinrm[0] = 1.0;
+            for (int k = 0; k < N; ++k) {
+                const double w = fmin(fmax(phi - thk, lim.omega_min), lim.omega_max);
+                S.om[k] = w;
+                thk = add_rn(thk, mul_rn(w, C.sampling_time));
+                S.th[k + 1] = thk;
+                const double vhi = fmin(lim.vmax0, lim.vmax0 - lim.alpha_over_pi * fabs(w));
+                S.vmid[k + 1] = 0.5 * (vhi + C.v_min0);
+                S.vhalf[k + 1] = 0.5 * (vhi - C.v_min0);
+                S.vinrm[k + 1] = 1.0 / (C.gtil * sqrt((double)(4 * k + 1)));   // |vel row k+1| = gtil sqrt(4(k+1)-3)
+            }
+            sc.status = LDCBF_STATUS_SOLVED; sc.iters = 0; sc.q = 0; sc.done = 0;
+        }
+        if (io.state6) {
+            const int f0 = io.state6[6 * (size_t)b + 5] < 0.0 ? -1 : 1;
+            for (int k = tid; k <= N; k += T) S.ft[k] = (k & 1) ? -f0 : f0;
+        } else {
+            for (int k = tid; k <= N; k += T) S.ft[k] = io.foot[(size_t)b * (N + 1) + k];
+        }
+        for (int i = tid; i < n * ld; i += T) S.J[i] = 0.0;
+        for (int i = tid; i < long_rsize(n); i += T) S.R[i] = 0.0;
+        for (int i = tid; i < nrows; i += T) S.act[i] = 0;
+        __syncthreads();
+        for (int k = tid; k <= N; k += T) {
+            sincos(S.th[k], &S.rs[k], &S.rc[k]);
+            S.P[2 * k] = k ? sc.gx : sc.p0x;
+            S.P[2 * k + 1] = k ? sc.gy : sc.p0y;
+        }
+        for (int i = tid; i < n; i += T) { S.J[i * ld + i] = 1.0; S.u[i] = 0.0; }
+        {
+            const double4* gce = reinterpret_cast<const double4*>(io.c_eta) + (size_t)b * max_obs;
+            for (int o = tid; o < nobs; o += T) {
+                const double4 c4 = gce[o];
+                S.ex[o] = c4.z; S.ey[o] = c4.w;
+                S.hb[o] = c4.z * c4.x + c4.w * c4.y + sc.delta;
+                S.eni[o] = rsqrt(c4.z * c4.z + c4.w * c4.w);
+                if (!(c4.z == c4.z) || !(c4.w == c4.w)) atomicMax(&sc.status, LDCBF_STATUS_DEGENERATE);
+                else if (c4.z * sc.p0x + c4.w * sc.p0y - S.hb[o] < -C.eps_const_row)     // constant k = 0 row
+                    atomicMax(&sc.status, LDCBF_STATUS_INFEASIBLE);
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && sc.status != LDCBF_STATUS_SOLVED) sc.done = 1;
+        __syncthreads();
+
+        // ------------------------------------------------------------------ active-set loop
+        while (!sc.done) {
+            // velocities at the iterate (x chain on thread 0, y chain on thread 1)
+            if (tid < 2) {
+                double v = tid ? sc.v0y : sc.v0x;
+                S.V[tid] = v;
+                for (int k = 0; k < N; ++k) {
+                    v = C.gtil * (S.P[2 * (k + 1) + tid] - S.P[2 * k + tid]) - v;
+                    S.V[2 * (k + 1) + tid] = v;
+                }
+            }
+            __syncthreads();
+            // most violated row, in units of distance to the row's hyperplane
+            double best = INFINITY;
+            int bid = INT_MAX;
+            for (int row = tid; row < nrows; row += T) {
+                if (S.act[row]) continue;
+                double sl, m, inrm;
+                long_eval_row(row, N, nobs, S, C, sc, sl, m, inrm);
+                sl *= inrm;
+                if (sl < best) { best = sl; bid = row; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bid, o);
+                if (ov < best || (ov == best && oi < bid)) { best = ov; bid = oi; }
+            }
+            if (lane == 0) { S.redv[warp] = best; S.redi[warp] = bid; }
+            __syncthreads();
+            if (tid == 0) {
+                for (int w = 1; w < T / 32; ++w)
+                    if (S.redv[w] < best || (S.redv[w] == best && S.redi[w] < bid)) { best = S.redv[w]; bid = S.redi[w]; }
+                if (!(best < -C.eps_active)) sc.done = 1;
+                else {
+                    double sl, m, inrm;
+                    long_eval_row(bid, N, nobs, S, C, sc, sl, m, inrm);
+                    const bool upper = bid < 4 * N && m >= 0.0;
+                    const double sg = upper ? -1.0 : 1.0;
+                    int typ, k;
+                    double rx, ry, kap2;
+                    if (bid < 2 * N) {
+                        typ = 0; k = (bid >> 1) + 1;                       // row ends at state k, heading k-1
+                        const double c = S.rc[k - 1], s = S.rs[k - 1];
+                        if ((bid & 1) == 0) { rx = c; ry = s; } else { rx = -s; ry = c; }
+                        kap2 = k > 1 ? 2.0 : 1.0;
+                    } else if (bid < 4 * N) {
+                        typ = 1; k = ((bid - 2 * N) >> 1) + 1;
+                        const double c = S.rc[k], s = S.rs[k];
+                        if ((bid & 1) == 0) { rx = c; ry = s; } else { rx = -s; ry = (double)S.ft[k] * c; }
+                        kap2 = C.gtil * C.gtil * (double)(4 * k - 3);
+                    } else {
+                        const int j = bid - 4 * N;
+                        typ = 2; k = j / nobs + 1;
+                        const int o = j - (k - 1) * nobs;
+                        rx = S.ex[o]; ry = S.ey[o];
+                        kap2 = 1.0;
+                    }
+                    sc.typ = typ; sc.k = k; sc.rx = sg * rx; sc.ry = sg * ry;
+                    sc.nn = (rx * rx + ry * ry) * kap2;
+                    sc.s_p = sl; sc.u_p = 0.0;
+                    sc.code = 2 * bid + (upper ? 1 : 0);
+                }
+                sc.inner_done = 0;
+            }
+            __syncthreads();
+            if (sc.done) break;
+
+            // ---- add row p: partial steps (dropping a row each) until the full step fits
+            while (true) {
+                const int q = sc.q;
+                const int typ = sc.typ, k = sc.k;
+                const double rx = sc.rx, ry = sc.ry;
+                // d = J^T n+ ; n+ has blocks kap_m (rx, ry) on p_m, m = m_lo..k
+                const int m_lo = typ == 2 ? k : (typ == 0 ? max(k - 1, 1) : 1);
+                for (int j = tid; j < n; j += T) {
+                    double acc = 0.0;
+                    for (int m = m_lo; m <= k; ++m) {
+                        double kap;
+                        if (typ == 1) kap = (m == k) ? C.gtil : (((k - m) & 1) ? -2.0 * C.gtil : 2.0 * C.gtil);
+                        else kap = (m == k) ? 1.0 : -1.0;
+                        const double* Jm = S.J + (size_t)(2 * (m - 1)) * ld + j;
+                        acc += kap * (rx * Jm[0] + ry * Jm[ld]);
+                    }
+                    S.d[j] = acc;
+                }
+                __syncthreads();
+                if (warp == 0) {
+                    // r = R^-1 d[0:q): column sweep, lane owns entries lane, lane+32, lane+64
+                    double dl0 = lane < q ? S.d[lane] : 0.0;
+                    double dl1 = lane + 32 < q ? S.d[lane + 32] : 0.0;
+                    double dl2 = lane + 64 < q ? S.d[lane + 64] : 0.0;
+                    for (int j = q - 1; j >= 0; --j) {
+                        const int e = j >> 5;
+                        const double mine = e == 0 ? dl0 : (e == 1 ? dl1 : dl2);
+                        const double rj = __shfl_sync(0xffffffffu, mine, j & 31) * S.rdi[j];
+                        if (lane == 0) S.r[j] = rj;
+                        const double* Rc = S.R + j;
+                        if (lane < j) dl0 -= Rc[long_rbase(lane, n)] * rj;
+                        if (lane + 32 < j) dl1 -= Rc[long_rbase(lane + 32, n)] * rj;
+                        if (lane + 64 < j) dl2 -= Rc[long_rbase(lane + 64, n)] * rj;
+                    }
+                    // |d[q:)|^2
+                    double acc = 0.0;
+                    for (int j = q + lane; j < n; j += 32) acc += S.d[j] * S.d[j];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    if (lane == 0) sc.d2n2 = acc;
+                } else {
+                    // z = J[:, q:) d[q:)
+                    for (int i = tid - 32; i < n; i += T - 32) {
+                        const double* Ji = S.J + (size_t)i * ld;
+                        double acc = 0.0;
+                        for (int j = q; j < n; ++j) acc += Ji[j] * S.d[j];
+                        S.z[i] = acc;
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    const int it = ++sc.iters;
+                    const double d2n2 = sc.d2n2;
+                    const bool dep = !(d2n2 > 1e-18 * sc.nn) || q == n;
+                    const double rtol = 1e-13 * sqrt(sc.nn);
+                    double t1n = 1.0, t1d = 0.0;
+                    int l = -1;
+                    for (int j = 0; j < q; ++j) {
+                        const double rj = S.r[j];
+                        if (rj > rtol && (l < 0 || S.u[j] * t1d < t1n * rj)) { t1n = S.u[j]; t1d = rj; l = j; }
+                    }
+                    const bool full = !dep && (l < 0 || (-sc.s_p) * t1d <= t1n * d2n2);
+                    sc.full = full; sc.dep = dep; sc.l = l;
+                    if (it > iter_cap) { sc.status = LDCBF_STATUS_MAX_ITER; sc.done = 1; sc.inner_done = 1; }
+                    else if (!full && l < 0) { sc.status = LDCBF_STATUS_INFEASIBLE; sc.done = 1; sc.inner_done = 1; }
+                    else {
+                        const double t = full ? (-sc.s_p) / d2n2 : fmax(t1n, 0.0) / t1d;
+                        sc.t = t;
+                        sc.u_p += t;
+                        if (!dep) sc.s_p += t * d2n2;
+                    }
+                }
+                __syncthreads();
+                if (sc.inner_done) break;
+                const double t = sc.t;
+                const bool full = sc.full, dep = sc.dep;
+                const int l = sc.l;
+                for (int j = tid; j < q; j += T) S.u[j] -= t * S.r[j];
+                if (!dep) for (int i = tid; i < n; i += T) S.P[2 + i] += t * S.z[i];
+                if (full) {
+                    // Householder reflection H = I - 2 v v^T / v^T v on the free columns, v = d[q:) - alpha e_0
+                    const double dq = S.d[q];
+                    const double alpha = dq > 0.0 ? -sqrt(sc.d2n2) : sqrt(sc.d2n2);
+                    const double v0 = dq - alpha;
+                    const double vn = sc.d2n2 - dq * dq + v0 * v0;
+                    const double two_over_vn = 2.0 / vn;
+                    for (int i = tid; i < n; i += T) {
+                        double* Ji = S.J + (size_t)i * ld;
+                        const double coef = (S.z[i] - alpha * Ji[q]) * two_over_vn;     // (J v)_i * 2 / |v|^2
+                        Ji[q] -= coef * v0;
+                        for (int j = q + 1; j < n; ++j) Ji[j] -= coef * S.d[j];
+                    }
+                    for (int i = tid; i < q; i += T) S.R[long_rbase(i, n) + q] = S.d[i];
+                    __syncthreads();            // every thread has read sc.q / sc.u_p before thread 0 moves on
+                    if (tid == 0) {
+                        S.R[long_rbase(q, n) + q] = alpha;
+                        S.rdi[q] = 1.0 / alpha;
+                        S.acode[q] = sc.code;
+                        S.u[q] = sc.u_p;
+                        S.act[sc.code >> 1] = 1;
+                        sc.q = q + 1;
+                    }
+                    __syncthreads();
+                    break;
+                }
+                // ---- partial step: row in position l leaves the active set
+                __syncthreads();                // u, P updated before the shifts below read u
+                for (int i = tid; i < q; i += T) {
+                    double* Ri = S.R + long_rbase(i, n);
+                    for (int c = max(l, i - 1); c < q - 1; ++c) Ri[c] = Ri[c + 1];
+                    Ri[q - 1] = 0.0;
+                }
+                if (tid == T - 1) {
+                    S.act[S.acode[l] >> 1] = 0;
+                    for (int c = l; c < q - 1; ++c) { S.u[c] = S.u[c + 1]; S.acode[c] = S.acode[c + 1]; }
+                    S.u[q - 1] = 0.0;
+                }
+                __syncthreads();
+                if (tid == 0 && l < q - 1) { sc.ab[l & 1][0] = S.R[long_rbase(l, n) + l]; sc.ab[l & 1][1] = S.R[long_rbase(l + 1, n) + l]; }
+                __syncthreads();
+                for (int i = l; i < q - 1; ++i) {
+                    // rotation on rows i, i+1 of R; thread tid owns column i + tid
+                    const double a = sc.ab[i & 1][0], bb = sc.ab[i & 1][1];
+                    const double h2 = a * a + bb * bb;
+                    const double inv = h2 > 0.0 ? rsqrt(h2) : 0.0;
+                    const double c_ = h2 > 0.0 ? a * inv : 1.0, s_ = bb * inv;
+                    for (int c = i + tid; c < q - 1; c += T) {
+                        double* Ra = S.R + long_rbase(i, n) + c;
+                        double* Rb = S.R + long_rbase(i + 1, n) + c;
+                        const double x = *Ra, y = *Rb;
+                        const double nx = c_ * x + s_ * y, ny = c_ * y - s_ * x;
+                        *Ra = nx;
+                        *Rb = (c == i) ? 0.0 : ny;
+                        if (c == i) { S.cs[i] = c_; S.sn[i] = s_; S.rdi[i] = 1.0 / nx; }
+                        if (c == i + 1) {
+                            sc.ab[(i + 1) & 1][0] = ny;
+                            sc.ab[(i + 1) & 1][1] = (i + 2 < q) ? S.R[long_rbase(i + 2, n) + c] : 0.0;
+                        }
+                    }
+                    __syncthreads();
+                }
+                // the same rotations on the columns of J: each thread walks its row
+                for (int r0 = tid; r0 < n; r0 += T) {
+                    double* Ji = S.J + (size_t)r0 * ld;
+                    double x = Ji[l];
+                    for (int i = l; i < q - 1; ++i) {
+                        const double y = Ji[i + 1];
+                        const double c_ = S.cs[i], s_ = S.sn[i];
+                        Ji[i] = c_ * x + s_ * y;
+                        x = c_ * y - s_ * x;
+                    }
+                    Ji[q - 1] = x;
+                }
+                if (tid == 0) sc.q = q - 1;
+                __syncthreads();
+            }
+            __syncthreads();
+        }
+
+        // ------------------------------------------------------------------ outputs
+        __syncthreads();
+        const bool ok = sc.status == LDCBF_STATUS_SOLVED;
+        if (tid < 2) {
+            double v = tid ? sc.v0y : sc.v0x;
+            S.V[tid] = v;
+            for (int k = 0; k < N; ++k) {
+                v = C.gtil * (S.P[2 * (k + 1) + tid] - S.P[2 * k + tid]) - v;
+                S.V[2 * (k + 1) + tid] = v;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double obj = 0.0;
+            for (int k = 0; k <= N; ++k) {
+                const double ex = S.P[2 * k] - sc.gx, ey = S.P[2 * k + 1] - sc.gy;
+                obj += ex * ex + ey * ey;
+            }
+            obj = ok ? obj : nan;
+            if (io.obj) io.obj[b] = obj;
+            if (io.status) io.status[b] = sc.status;
+            if (io.iters) io.iters[b] = sc.iters;
+            if (io.next10) {
+                double* o = io.next10 + 10 * (size_t)b;
+                const double u0x = (S.P[2] - C.ch * S.P[0] - C.sh_over_beta * S.V[0]) * C.inv_one_m_ch;
+                const double u0y = (S.P[3] - C.ch * S.P[1] - C.sh_over_beta * S.V[1]) * C.inv_one_m_ch;
+                o[0] = ok ? S.P[2] : nan; o[1] = ok ? S.V[2] : nan; o[2] = ok ? S.P[3] : nan; o[3] = ok ? S.V[3] : nan;
+                o[4] = S.th[1]; o[5] = ok ? u0x : nan; o[6] = ok ? u0y : nan; o[7] = S.om[0];
+                o[8] = obj; o[9] = (double)sc.status;
+            }
+        }
+        if (io.U) {
+            for (int k = tid; k <= N; k += T) {
+                const bool live = ok || k == 0;
+                double4 xk = make_double4(S.P[2 * k], S.V[2 * k], S.P[2 * k + 1], S.V[2 * k + 1]);
+                if (!live) xk = make_double4(nan, nan, nan, nan);
+                reinterpret_cast<double4*>(io.X)[(size_t)b * (N + 1) + k] = xk;
+                io.theta[(size_t)b * (N + 1) + k] = S.th[k];
+                if (k < N) {
+                    const double ux = (S.P[2 * (k + 1)] - C.ch * S.P[2 * k] - C.sh_over_beta * S.V[2 * k]) * C.inv_one_m_ch;
+                    const double uy = (S.P[2 * (k + 1) + 1] - C.ch * S.P[2 * k + 1] - C.sh_over_beta * S.V[2 * k + 1]) * C.inv_one_m_ch;
+                    reinterpret_cast<double2*>(io.U)[(size_t)b * N + k] = ok ? make_double2(ux, uy) : make_double2(nan, nan);
+                    io.omega[(size_t)b * N + k] = S.om[k];
+                }
+            }
+        }
+    }
+}
+
+template <int T>
+static int launch_long(const StepConst& C, int B, int N, int max_obs, const StepIO& io, cudaStream_t st) {
+    const size_t smem = long_carve(N, max_obs, nullptr, nullptr);
+    if (smem > 227 * 1024) return LDCBF_E_SHAPE;
+    auto kern = mpc_long_kernel<T>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_last_error(e); return LDCBF_E_LAUNCH; }
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 2048 / T ? 2048 / T : per_sm);
+    const int grid = B < 148 * per_sm ? B : 148 * per_sm;
+    const int iter_cap = C.max_iter * ((N + 3) / 4);
+    kern<<<grid, T, smem, st>>>(C, B, N, max_obs, iter_cap, io);
+    return check_launch();
+}
+
+int launch_long_horizon(const StepConst& C, int B, int N, int max_obs, const StepIO& io, cudaStream_t st) {
+    if (N > LDCBF_MAX_HORIZON_LONG) return LDCBF_E_SHAPE;
+    return 2 * N <= 32 ? launch_long<64>(C, B, N, max_obs, io, st) : launch_long<128>(C, B, N, max_obs, io, st);
+}
+
+}  // namespace ldcbf

@@ -3,6 +3,7 @@
 #include <mutex>
 
 #include "mpc_qp.cuh"
+#include "step_io.cuh"
 
 #ifndef LDCBF_QP_REFILL_TRIPS
 #define LDCBF_QP_REFILL_TRIPS 1
@@ -15,26 +16,6 @@ namespace ldcbf {
 
 static thread_local cudaError_t g_last_error = cudaSuccess;
 void set_last_error(cudaError_t e) { g_last_error = e; }
-
-struct StepIO {
-    const double* x0; const double* theta0; const double* goal; const int8_t* foot;
-    const double* c_eta; const int32_t* nobs; const double* delta; const double* limits;
-    double* U; double* X; double* theta; double* omega; double* obj; int32_t* status; int32_t* iters;
-    // loop-shaped variant (ldcbf_mpc_step_packed_f64): state rows [B,6] in (x0/theta0/foot unused), next rows [B,10] out
-    const double* state6; double* next10;
-};
-
-__device__ __forceinline__ void load_state(const StepIO& io, int b, double4& x, double& th) {
-    if (io.state6) {
-        const double2* s = reinterpret_cast<const double2*>(io.state6) + 3 * (size_t)b;
-        const double2 a = s[0], c = s[1], e = s[2];
-        x = make_double4(a.x, a.y, c.x, c.y);
-        th = e.x;
-    } else {
-        x = reinterpret_cast<const double4*>(io.x0)[b];          // (p_x, v_x, p_y, v_y)
-        th = io.theta0[b];
-    }
-}
 
 template <int N>
 __device__ __forceinline__ void store_solution(const QpSolution<N>& S, int b, const StepIO& io) {
@@ -217,7 +198,7 @@ static int dispatch_horizon(const ldcbf_params& prm, int B, int N, int max_obs, 
         case 2: return dispatch_obs<2>(C, B, max_obs, io, st);
         case 3: return dispatch_obs<3>(C, B, max_obs, io, st);
         case 4: return dispatch_obs<4>(C, B, max_obs, io, st);
-        default: return LDCBF_E_SHAPE;
+        default: return N > LDCBF_MAX_HORIZON ? launch_long_horizon(C, B, N, max_obs, io, st) : LDCBF_E_SHAPE;
     }
 }
 

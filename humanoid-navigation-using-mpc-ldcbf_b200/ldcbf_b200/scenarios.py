@@ -153,3 +153,33 @@ def config4(B=8192, seed=0, n_goals=6):
     verts, nverts, nobs = pack_rings([[wall]] * B, 1, 4)
     return dict(state=np.zeros((B, 5)), goals=goals, verts=verts, nverts=nverts, nobs=nobs,
                 right_first=np.ones(B, dtype=bool), rings=[wall])
+
+
+def config5(B=1024, n_obs=8, seed=0, pool=32):
+    """Scaling sweep: `n_obs` regular octagons of radius 0.3 on a jittered grid over [1,9]^2
+    (the MAIN_PAPER extent of `report_simulations/Scenario.py:220-222`), goal (10,10); one open-loop step per scenario
+    from a random obstacle-free position in [0,10]^2 at rest with a random heading and first foot.  `pool` distinct
+    maps are generated and tiled to B scenarios.
+    Returns dict(state[B,5], goal[B,2], right_first[B], verts[B,n_obs,8,2], nverts, nobs, rings (pool lists), map_index)."""
+    rng = np.random.default_rng(seed)
+    side = int(math.ceil(math.sqrt(n_obs)))
+    pitch = 8.0 / side
+    ang = np.arange(8) * (2 * np.pi / 8)
+    maps, centres = [], []
+    for _ in range(pool):
+        cells = rng.permutation(side * side)[:n_obs]
+        c = np.column_stack((1 + (cells % side + 0.5) * pitch, 1 + (cells // side + 0.5) * pitch))
+        c += rng.uniform(-0.15, 0.15, c.shape) * pitch
+        centres.append(c)
+        maps.append([np.column_stack((cc[0] + 0.3 * np.cos(ang), cc[1] + 0.3 * np.sin(ang))) for cc in c])
+    verts_p, nverts_p, nobs_p = pack_rings(maps, n_obs, 8)
+    idx = np.arange(B) % pool
+    state = np.zeros((B, 5))
+    for b in range(B):
+        while True:
+            p = rng.uniform(0, 10, 2)
+            if np.min(np.hypot(*(centres[idx[b]] - p).T)) > 0.45:
+                break
+        state[b] = (p[0], 0.0, p[1], 0.0, rng.uniform(-math.pi, math.pi))
+    return dict(state=state, goal=np.tile([10.0, 10.0], (B, 1)), right_first=rng.random(B) < 0.5, verts=verts_p[idx],
+                nverts=nverts_p[idx], nobs=nobs_p[idx], rings=maps, map_index=idx)

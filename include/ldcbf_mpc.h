@@ -41,9 +41,12 @@ extern "C" {
 #define LDCBF_STATUS_DEGENERATE 3   /* CoM exactly on an obstacle edge: ||x-c|| = 0 (ObstaclesUtils.py:104) */
 #define LDCBF_STATUS_DONE 4         /* rollout only: scenario already stopped (objective < stop_objective) */
 
-/* supported shapes: horizon 1..4 (register-resident solver); any number of obstacles per scenario in
- * ldcbf_mpc_qp_f64 / ldcbf_mpc_step_f64 (the first 8 in registers, the rest streamed), at most 8 in ldcbf_rollout_f64 */
+/* supported shapes: horizon 1..4 by the register-resident solver (one thread per scenario) and 5..48 by the
+ * long-horizon solver (one thread block per scenario, iteration cap max_iter * ceil(N / 4)); any number of
+ * obstacles per scenario in ldcbf_mpc_qp_f64 / ldcbf_mpc_step_f64 (as far as shared memory holds N * max_obs row
+ * flags for the long horizons: 64 obstacles at N = 48), at most 8 obstacles and horizon 4 in ldcbf_rollout_f64 */
 #define LDCBF_MAX_HORIZON 4
+#define LDCBF_MAX_HORIZON_LONG 48
 #define LDCBF_MAX_OBSTACLES 8
 
 /* Every key of HumanoidNavigation/config.yml:2-17 that the hot path reads, the constants the reference
