@@ -99,7 +99,8 @@ class HumanoidMPC:
                        fill_animator: bool = True, initial_animator=None):
         """Returns (X_pred[5,K+1], U_pred[3,K], animator) like the reference (:345-494); animator is passed through
         (plotting is out of scope)."""
-        if self._hooks_overridden() or len(self.obstacles) > ldcbf_b200.binding.MAX_OBSTACLES:
+        if (self._hooks_overridden() or len(self.obstacles) > ldcbf_b200.binding.MAX_OBSTACLES
+                or self.N_horizon > ldcbf_b200.binding.MAX_HORIZON):      # long horizons: block-per-scenario step kernel
             X_pred, U_pred = self._run_stepwise()
         else:
             X_pred, U_pred = self._run_fused()

@@ -69,7 +69,7 @@ __host__ __device__ inline size_t long_carve(int N, int max_obs, char* base, Lon
 
 struct LongScalars {
     double p0x, p0y, v0x, v0y, gx, gy, delta, vlat_mid, vlat_half;
-    double rx, ry, nn, s_p, u_p, t, d2n2, ab[2][2];
+    double rx, ry, nn, s_p, u_p, t, t1, d2n2;
     int q, status, iters, done, typ, k, code, full, dep, l, inner_done;
 };
 
@@ -96,6 +96,23 @@ __device__ __forceinline__ void long_eval_row(int row, int N, int nobs, const Lo
         slack = S.ex[o] * S.P[2 * kk] + S.ey[o] * S.P[2 * kk + 1] - S.hb[o];
         m = -1.0;
         inrm = S.eni[o];
+    }
+}
+
+// v_k = (-1)^k v_0 + gtil sum_{j<k} (-1)^{k-1-j} (p_{j+1} - p_j): one thread per (state, axis), two accumulators.
+template <int T>
+__device__ __forceinline__ void long_velocities(int N, double gtil, const LongShared& S, const LongScalars& sc) {
+    for (int e = threadIdx.x; e < 2 * (N + 1); e += T) {
+        const int k = e >> 1, ax = e & 1;
+        double even = 0.0, odd = 0.0;          // sums over j with k-1-j even / odd
+        int j = k - 1;
+        for (; j >= 1; j -= 2) {
+            even += S.P[2 * (j + 1) + ax] - S.P[2 * j + ax];
+            odd += S.P[2 * j + ax] - S.P[2 * (j - 1) + ax];
+        }
+        if (j == 0) even += S.P[2 + ax] - S.P[ax];
+        const double v0 = ax ? sc.v0y : sc.v0x;
+        S.V[e] = ((k & 1) ? -v0 : v0) + gtil * (even - odd);
     }
 }
 
@@ -172,15 +189,8 @@ __global__ void __launch_bounds__(T) mpc_long_kernel(StepConst C, int B, int N, 
 
         // ------------------------------------------------------------------ active-set loop
         while (!sc.done) {
-            // velocities at the iterate (x chain on thread 0, y chain on thread 1)
-            if (tid < 2) {
-                double v = tid ? sc.v0y : sc.v0x;
-                S.V[tid] = v;
-                for (int k = 0; k < N; ++k) {
-                    v = C.gtil * (S.P[2 * (k + 1) + tid] - S.P[2 * k + tid]) - v;
-                    S.V[2 * (k + 1) + tid] = v;
-                }
-            }
+            // velocities at the iterate
+            long_velocities<T>(N, C.gtil, S, sc);
             __syncthreads();
             // most violated row, in units of distance to the row's hyperplane
             double best = INFINITY;
@@ -258,26 +268,66 @@ __global__ void __launch_bounds__(T) mpc_long_kernel(StepConst C, int B, int N, 
                 }
                 __syncthreads();
                 if (warp == 0) {
-                    // r = R^-1 d[0:q): column sweep, lane owns entries lane, lane+32, lane+64
+                    // r = R^-1 d[0:q): column sweep in blocks of four columns; lane owns entries lane, lane+32, lane+64
+                    // (a solved entry stays in its owner's register as r_j).  Only the shuffles and the small 4x4
+                    // substitution are on the dependent chain; every shared-memory load is address-independent.
                     double dl0 = lane < q ? S.d[lane] : 0.0;
                     double dl1 = lane + 32 < q ? S.d[lane + 32] : 0.0;
                     double dl2 = lane + 64 < q ? S.d[lane + 64] : 0.0;
-                    for (int j = q - 1; j >= 0; --j) {
+                    const int rb0 = long_rbase(lane, n), rb1 = long_rbase(lane + 32, n), rb2 = long_rbase(lane + 64, n);
+                    auto pick = [&](int j) {
                         const int e = j >> 5;
-                        const double mine = e == 0 ? dl0 : (e == 1 ? dl1 : dl2);
-                        const double rj = __shfl_sync(0xffffffffu, mine, j & 31) * S.rdi[j];
-                        if (lane == 0) S.r[j] = rj;
-                        const double* Rc = S.R + j;
-                        if (lane < j) dl0 -= Rc[long_rbase(lane, n)] * rj;
-                        if (lane + 32 < j) dl1 -= Rc[long_rbase(lane + 32, n)] * rj;
-                        if (lane + 64 < j) dl2 -= Rc[long_rbase(lane + 64, n)] * rj;
+                        return __shfl_sync(0xffffffffu, e == 0 ? dl0 : (e == 1 ? dl1 : dl2), j & 31);
+                    };
+                    auto put = [&](int j, double v) {
+                        if (lane == (j & 31)) { const int e = j >> 5; if (e == 0) dl0 = v; else if (e == 1) dl1 = v; else dl2 = v; }
+                    };
+                    int j = q - 1;
+                    for (; j >= 3; j -= 4) {
+                        const double a0 = pick(j), a1 = pick(j - 1), a2 = pick(j - 2), a3 = pick(j - 3);
+                        const double* R1 = S.R + long_rbase(j - 1, n);
+                        const double* R2 = S.R + long_rbase(j - 2, n);
+                        const double* R3 = S.R + long_rbase(j - 3, n);
+                        const double r0 = a0 * S.rdi[j];
+                        const double r1 = (a1 - R1[j] * r0) * S.rdi[j - 1];
+                        const double r2 = (a2 - R2[j] * r0 - R2[j - 1] * r1) * S.rdi[j - 2];
+                        const double r3 = (a3 - R3[j] * r0 - R3[j - 1] * r1 - R3[j - 2] * r2) * S.rdi[j - 3];
+                        put(j, r0); put(j - 1, r1); put(j - 2, r2); put(j - 3, r3);
+                        if (lane < j - 3) { const double* Rr = S.R + rb0 + j; dl0 -= Rr[0] * r0 + Rr[-1] * r1 + Rr[-2] * r2 + Rr[-3] * r3; }
+                        if (lane + 32 < j - 3) { const double* Rr = S.R + rb1 + j; dl1 -= Rr[0] * r0 + Rr[-1] * r1 + Rr[-2] * r2 + Rr[-3] * r3; }
+                        if (lane + 64 < j - 3) { const double* Rr = S.R + rb2 + j; dl2 -= Rr[0] * r0 + Rr[-1] * r1 + Rr[-2] * r2 + Rr[-3] * r3; }
+                    }
+                    for (; j >= 0; --j) {
+                        const double rj = pick(j) * S.rdi[j];
+                        put(j, rj);
+                        if (lane < j) dl0 -= S.R[rb0 + j] * rj;
+                        if (lane + 32 < j) dl1 -= S.R[rb1 + j] * rj;
+                        if (lane + 64 < j) dl2 -= S.R[rb2 + j] * rj;
+                    }
+                    // dual step length t1 = min u_j / r_j over r_j > 0 (ties: lowest position)
+                    const double rtol = 1e-13 * sqrt(sc.nn);
+                    double t1 = INFINITY;
+                    int l1 = INT_MAX;
+                    if (lane < q) { S.r[lane] = dl0; if (dl0 > rtol) { t1 = fmax(S.u[lane], 0.0) / dl0; l1 = lane; } }
+                    if (lane + 32 < q) {
+                        S.r[lane + 32] = dl1;
+                        if (dl1 > rtol) { const double v = fmax(S.u[lane + 32], 0.0) / dl1; if (v < t1) { t1 = v; l1 = lane + 32; } }
+                    }
+                    if (lane + 64 < q) {
+                        S.r[lane + 64] = dl2;
+                        if (dl2 > rtol) { const double v = fmax(S.u[lane + 64], 0.0) / dl2; if (v < t1) { t1 = v; l1 = lane + 64; } }
                     }
                     // |d[q:)|^2
                     double acc = 0.0;
-                    for (int j = q + lane; j < n; j += 32) acc += S.d[j] * S.d[j];
+                    for (int jj = q + lane; jj < n; jj += 32) acc += S.d[jj] * S.d[jj];
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                    if (lane == 0) sc.d2n2 = acc;
+                    for (int o = 16; o > 0; o >>= 1) {
+                        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                        const double ov = __shfl_xor_sync(0xffffffffu, t1, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, l1, o);
+                        if (ov < t1 || (ov == t1 && oi < l1)) { t1 = ov; l1 = oi; }
+                    }
+                    if (lane == 0) { sc.d2n2 = acc; sc.t1 = t1; sc.l = l1 == INT_MAX ? -1 : l1; }
                 } else {
                     // z = J[:, q:) d[q:)
                     for (int i = tid - 32; i < n; i += T - 32) {
@@ -292,19 +342,14 @@ __global__ void __launch_bounds__(T) mpc_long_kernel(StepConst C, int B, int N, 
                     const int it = ++sc.iters;
                     const double d2n2 = sc.d2n2;
                     const bool dep = !(d2n2 > 1e-18 * sc.nn) || q == n;
-                    const double rtol = 1e-13 * sqrt(sc.nn);
-                    double t1n = 1.0, t1d = 0.0;
-                    int l = -1;
-                    for (int j = 0; j < q; ++j) {
-                        const double rj = S.r[j];
-                        if (rj > rtol && (l < 0 || S.u[j] * t1d < t1n * rj)) { t1n = S.u[j]; t1d = rj; l = j; }
-                    }
-                    const bool full = !dep && (l < 0 || (-sc.s_p) * t1d <= t1n * d2n2);
-                    sc.full = full; sc.dep = dep; sc.l = l;
+                    const int l = sc.l;
+                    const double t2 = dep ? INFINITY : (-sc.s_p) / d2n2;
+                    const bool full = !dep && (l < 0 || t2 <= sc.t1);
+                    sc.full = full; sc.dep = dep;
                     if (it > iter_cap) { sc.status = LDCBF_STATUS_MAX_ITER; sc.done = 1; sc.inner_done = 1; }
                     else if (!full && l < 0) { sc.status = LDCBF_STATUS_INFEASIBLE; sc.done = 1; sc.inner_done = 1; }
                     else {
-                        const double t = full ? (-sc.s_p) / d2n2 : fmax(t1n, 0.0) / t1d;
+                        const double t = full ? t2 : sc.t1;
                         sc.t = t;
                         sc.u_p += t;
                         if (!dep) sc.s_p += t * d2n2;
@@ -356,29 +401,56 @@ __global__ void __launch_bounds__(T) mpc_long_kernel(StepConst C, int B, int N, 
                     S.u[q - 1] = 0.0;
                 }
                 __syncthreads();
-                if (tid == 0 && l < q - 1) { sc.ab[l & 1][0] = S.R[long_rbase(l, n) + l]; sc.ab[l & 1][1] = S.R[long_rbase(l + 1, n) + l]; }
-                __syncthreads();
-                for (int i = l; i < q - 1; ++i) {
-                    // rotation on rows i, i+1 of R; thread tid owns column i + tid
-                    const double a = sc.ab[i & 1][0], bb = sc.ab[i & 1][1];
-                    const double h2 = a * a + bb * bb;
-                    const double inv = h2 > 0.0 ? rsqrt(h2) : 0.0;
-                    const double c_ = h2 > 0.0 ? a * inv : 1.0, s_ = bb * inv;
-                    for (int c = i + tid; c < q - 1; c += T) {
-                        double* Ra = S.R + long_rbase(i, n) + c;
-                        double* Rb = S.R + long_rbase(i + 1, n) + c;
-                        const double x = *Ra, y = *Rb;
-                        const double nx = c_ * x + s_ * y, ny = c_ * y - s_ * x;
-                        *Ra = nx;
-                        *Rb = (c == i) ? 0.0 : ny;
-                        if (c == i) { S.cs[i] = c_; S.sn[i] = s_; S.rdi[i] = 1.0 / nx; }
-                        if (c == i + 1) {
-                            sc.ab[(i + 1) & 1][0] = ny;
-                            sc.ab[(i + 1) & 1][1] = (i + 2 < q) ? S.R[long_rbase(i + 2, n) + c] : 0.0;
+                if (warp == 0) {
+                    // Rotations i = l..q-2 on rows (i, i+1) of R.  Lane owns columns l + lane + 32 e; the upper-row
+                    // entry of each owned column is carried in a register from one rotation to the next, the
+                    // lower-row entries are untouched until their rotation (loaded one rotation ahead), and the
+                    // pivot pair travels by shuffle: the dependent chain per rotation is shuffle -> rsqrt -> two FMAs.
+                    const int c0 = l + lane, c1 = c0 + 32, c2 = c0 + 64, qe = q - 1;
+                    const int rbl = long_rbase(l, n);
+                    double x0 = c0 < qe ? S.R[rbl + c0] : 0.0, x1 = c1 < qe ? S.R[rbl + c1] : 0.0, x2 = c2 < qe ? S.R[rbl + c2] : 0.0;
+                    int rbn = l + 1 < n ? long_rbase(l + 1, n) : 0;
+                    double y0 = (c0 < qe && l + 1 <= c0 + 1) ? S.R[rbn + c0] : 0.0;
+                    double y1 = (c1 < qe) ? S.R[rbn + c1] : 0.0;
+                    double y2 = (c2 < qe) ? S.R[rbn + c2] : 0.0;
+                    for (int i = l; i < qe; ++i) {
+                        const int rbi = long_rbase(i, n), rbi1 = rbn;
+                        // prefetch the lower row of the next rotation (row i+2), only where it is stored (c >= i+1)
+                        double yn0 = 0.0, yn1 = 0.0, yn2 = 0.0;
+                        if (i + 1 < qe) {
+                            rbn = long_rbase(i + 2, n);
+                            if (c0 < qe && c0 >= i + 1) yn0 = S.R[rbn + c0];
+                            if (c1 < qe && c1 >= i + 1) yn1 = S.R[rbn + c1];
+                            if (c2 < qe && c2 >= i + 1) yn2 = S.R[rbn + c2];
                         }
+                        const int e = (i - l) >> 5, src = (i - l) & 31;
+                        const double a = __shfl_sync(0xffffffffu, e == 0 ? x0 : (e == 1 ? x1 : x2), src);
+                        const double bb = __shfl_sync(0xffffffffu, e == 0 ? y0 : (e == 1 ? y1 : y2), src);
+                        const double h2 = a * a + bb * bb;
+                        const double inv = h2 > 0.0 ? rsqrt_f64(h2) : 0.0;
+                        const double c_ = h2 > 0.0 ? a * inv : 1.0, s_ = bb * inv;
+                        if (c0 >= i && c0 < qe) {
+                            const double nx = c_ * x0 + s_ * y0;
+                            S.R[rbi + c0] = nx;
+                            if (c0 == i) { S.R[rbi1 + c0] = 0.0; S.cs[i] = c_; S.sn[i] = s_; S.rdi[i] = inv; }
+                            x0 = c_ * y0 - s_ * x0;
+                        }
+                        if (c1 >= i && c1 < qe) {
+                            const double nx = c_ * x1 + s_ * y1;
+                            S.R[rbi + c1] = nx;
+                            if (c1 == i) { S.R[rbi1 + c1] = 0.0; S.cs[i] = c_; S.sn[i] = s_; S.rdi[i] = inv; }
+                            x1 = c_ * y1 - s_ * x1;
+                        }
+                        if (c2 >= i && c2 < qe) {
+                            const double nx = c_ * x2 + s_ * y2;
+                            S.R[rbi + c2] = nx;
+                            if (c2 == i) { S.R[rbi1 + c2] = 0.0; S.cs[i] = c_; S.sn[i] = s_; S.rdi[i] = inv; }
+                            x2 = c_ * y2 - s_ * x2;
+                        }
+                        y0 = yn0; y1 = yn1; y2 = yn2;
                     }
-                    __syncthreads();
                 }
+                __syncthreads();
                 // the same rotations on the columns of J: each thread walks its row
                 for (int r0 = tid; r0 < n; r0 += T) {
                     double* Ji = S.J + (size_t)r0 * ld;
@@ -400,14 +472,7 @@ __global__ void __launch_bounds__(T) mpc_long_kernel(StepConst C, int B, int N, 
         // ------------------------------------------------------------------ outputs
         __syncthreads();
         const bool ok = sc.status == LDCBF_STATUS_SOLVED;
-        if (tid < 2) {
-            double v = tid ? sc.v0y : sc.v0x;
-            S.V[tid] = v;
-            for (int k = 0; k < N; ++k) {
-                v = C.gtil * (S.P[2 * (k + 1) + tid] - S.P[2 * k + tid]) - v;
-                S.V[2 * (k + 1) + tid] = v;
-            }
-        }
+        long_velocities<T>(N, C.gtil, S, sc);
         __syncthreads();
         if (tid == 0) {
             double obj = 0.0;

@@ -10,6 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LDCBF_B200_LIB") or os.path.join(_HERE, "libldcbf_b200.so")   # env override: A/B builds
 
 MAX_OBSTACLES = 8      # LDCBF_MAX_OBSTACLES of include/ldcbf_mpc.h
+MAX_HORIZON = 4        # LDCBF_MAX_HORIZON: fused rollout / thread-per-scenario solver
+MAX_HORIZON_LONG = 48  # LDCBF_MAX_HORIZON_LONG: block-per-scenario solver for 5..48
 
 EXPORTS = ("ldcbf_abi_version", "ldcbf_params_default", "ldcbf_last_cuda_error", "ldcbf_workspace_bytes",
            "ldcbf_halfplanes_f64", "ldcbf_mpc_qp_f64", "ldcbf_mpc_step_f64", "ldcbf_mpc_step_packed_f64",

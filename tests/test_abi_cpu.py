@@ -60,6 +60,12 @@ def test_argument_errors_without_device(lib):
     assert lib.ldcbf_halfplanes_f64(4, 0, 24, None, None, None, None, None, None) == -1
     assert lib.ldcbf_mpc_qp_f64(ctypes.byref(p), 2, 3, 3, *([None] * 16)) == -1
     assert lib.ldcbf_mpc_qp_f64(None, 2, 3, 3, *([None] * 16)) == -1
+    # horizons 1..4 and 5..48 are served; beyond that LDCBF_E_SHAPE, decided before anything touches the device
+    dummy = (ctypes.c_double * 8)()
+    ptrs = [ctypes.cast(dummy, ctypes.c_void_p)] * 15
+    for n_h, want in ((49, -2), (0, -2), (-3, -2)):
+        args = ptrs[:6] + [None, None] + ptrs[:7] + [None]
+        assert lib.ldcbf_mpc_qp_f64(ctypes.byref(p), 2, n_h, 3, *args) == want
     assert lib.ldcbf_mpc_step_f64(ctypes.byref(p), 0, 3, 3, 24, *([None] * 19)) == 0
     assert lib.ldcbf_mpc_step_packed_f64(ctypes.byref(p), 4, 3, 3, 24, *([None] * 11)) == -1
     assert lib.ldcbf_lidar_cast_f64(1, 0, None, 1.5, None, 3, 24, None, None, None, None, None, None, None) == -1
