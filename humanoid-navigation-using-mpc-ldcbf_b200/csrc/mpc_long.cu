@@ -22,11 +22,22 @@
 
 namespace ldcbf {
 
+// Development aid: -DLDCBF_LONG_PROFILE accumulates thread-0 cycle counts per phase of the active-set loop
+// (read back with ldcbf_debug_long_profile); compiled out of the product library.
+#ifdef LDCBF_LONG_PROFILE
+__device__ unsigned long long g_long_prof[16];
+#define PROF_DECL long long prof_t = clock64(); unsigned long long prof_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define PROF(i) { const long long now_ = clock64(); prof_acc[i] += (unsigned long long)(now_ - prof_t); prof_t = now_; }
+#define PROF_FLUSH if (threadIdx.x == 0) { for (int i_ = 0; i_ < 12; ++i_) atomicAdd(&g_long_prof[i_], prof_acc[i_]); }
+#else
+#define PROF_DECL
+#define PROF(i)
+#define PROF_FLUSH
+#endif
+
 // R is stored packed: row i keeps the columns c >= i-1 (the triangle plus the one sub-diagonal that exists while a
-// column is being deleted); element (i, c) lives at R[long_rbase(i, n) + c].
-__host__ __device__ __forceinline__ int long_rbase(int i, int n) {
-    return i == 0 ? 0 : n + (i - 1) * (n + 1) - ((i - 1) * i) / 2 - (i - 1);
-}
+// column is being deleted); element (i, c) lives at R[long_rbase(i, n) + c], and rbase(i+1) - rbase(i) = n - i.
+__host__ __device__ __forceinline__ int long_rbase(int i, int n) { return n * i - (i * (i - 1)) / 2; }
 __host__ __device__ __forceinline__ int long_rsize(int n) { return n + (n - 1) * (n + 1) - ((n - 1) * n) / 2; }
 
 struct LongShared {
@@ -99,6 +110,46 @@ __device__ __forceinline__ void long_eval_row(int row, int N, int nobs, const Lo
     }
 }
 
+// Solves rows [lo, hi) (hi - lo <= 32) of the upper-triangular system R r = rhs inside one warp: lane owns row
+// lo + lane (`me`: right-hand side in, solution out), columns swept from hi-1 down, four at a time.  The dependent
+// chain per group of four is shuffle -> 4x4 substitution -> one fused update; all shared-memory loads are
+// address-independent of it.
+__device__ __forceinline__ double long_tri32(const double* __restrict__ R, const double* __restrict__ rdi, int n, int lo,
+                                             int hi, int lane, double me) {
+    const double* Rme = R + long_rbase(lo + lane, n) + lo;      // my row, indexed by pivot lane
+    int p = hi - lo - 1;
+    for (; p >= 0 && (p & 3) != 3; --p) {
+        const double rj = __shfl_sync(0xffffffffu, me, p) * rdi[lo + p];
+        if (lane == p) me = rj;
+        if (lane < p) me -= Rme[p] * rj;
+    }
+    for (; p >= 3; p -= 4) {
+        const int j = lo + p;
+        const double a0 = __shfl_sync(0xffffffffu, me, p), a1 = __shfl_sync(0xffffffffu, me, p - 1);
+        const double a2 = __shfl_sync(0xffffffffu, me, p - 2), a3 = __shfl_sync(0xffffffffu, me, p - 3);
+        const double* R1 = R + long_rbase(j - 1, n) + j;
+        const double* R2 = R1 - (n - (j - 2));                  // rbase(i) - rbase(i-1) = n - (i-1) for i >= 2
+        const double* R3 = R2 - (n - (j - 3));
+        // partial sums advance as soon as each r is known: the chain is mul, (fma, mul) x 3, fma
+        const bool upd = lane < p - 3;
+        const double m0 = upd ? Rme[p] : 0.0, m1 = upd ? Rme[p - 1] : 0.0, m2 = upd ? Rme[p - 2] : 0.0, m3 = upd ? Rme[p - 3] : 0.0;
+        const double r0 = a0 * rdi[j];
+        double b1 = a1 - R1[0] * r0, b2 = a2 - R2[0] * r0, b3 = a3 - R3[0] * r0, mm = me - m0 * r0;
+        const double r1 = b1 * rdi[j - 1];
+        b2 -= R2[-1] * r1; b3 -= R3[-1] * r1; mm -= m1 * r1;
+        const double r2 = b2 * rdi[j - 2];
+        b3 -= R3[-2] * r2; mm -= m2 * r2;
+        const double r3 = b3 * rdi[j - 3];
+        mm -= m3 * r3;
+        me = mm;
+        if (lane == p) me = r0;
+        if (lane == p - 1) me = r1;
+        if (lane == p - 2) me = r2;
+        if (lane == p - 3) me = r3;
+    }
+    return me;
+}
+
 // v_k = (-1)^k v_0 + gtil sum_{j<k} (-1)^{k-1-j} (p_{j+1} - p_j): one thread per (state, axis), two accumulators.
 template <int T>
 __device__ __forceinline__ void long_velocities(int N, double gtil, const LongShared& S, const LongScalars& sc) {
@@ -116,8 +167,8 @@ __device__ __forceinline__ void long_velocities(int N, double gtil, const LongSh
     }
 }
 
-template <int T>
-__global__ void __launch_bounds__(T) mpc_long_kernel(StepConst C, int B, int N, int max_obs, int iter_cap, StepIO io) {
+template <int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) mpc_long_kernel(StepConst C, int B, int N, int max_obs, int iter_cap, StepIO io) {
     extern __shared__ __align__(16) char long_smem[];
     __shared__ LongScalars sc;
     LongShared S;
@@ -126,8 +177,10 @@ __global__ void __launch_bounds__(T) mpc_long_kernel(StepConst C, int B, int N, 
     const int n = 2 * N, ld = n | 1;
     const double nan = quiet_nan();
 
+    PROF_DECL
     for (int b = blockIdx.x; b < B; b += gridDim.x) {
         __syncthreads();
+        PROF(0)
         const int nobs = min(io.nobs[b], max_obs);
         const int nrows = 4 * N + N * nobs;
         // ------------------------------------------------------------------ setup
@@ -188,19 +241,34 @@ __global__ void __launch_bounds__(T) mpc_long_kernel(StepConst C, int B, int N, 
         __syncthreads();
 
         // ------------------------------------------------------------------ active-set loop
+        PROF(1)
         while (!sc.done) {
             // velocities at the iterate
             long_velocities<T>(N, C.gtil, S, sc);
             __syncthreads();
+            PROF(2)
             // most violated row, in units of distance to the row's hyperplane
             double best = INFINITY;
             int bid = INT_MAX;
-            for (int row = tid; row < nrows; row += T) {
+            for (int row = tid; row < 4 * N; row += T) {
                 if (S.act[row]) continue;
                 double sl, m, inrm;
                 long_eval_row(row, N, nobs, S, C, sc, sl, m, inrm);
                 sl *= inrm;
                 if (sl < best) { best = sl; bid = row; }
+            }
+            if (nobs > 0) {                                  // LDCBF rows (k, o), o fastest; (k, o) advanced without a division
+                const int dk = T / nobs, dob = T - dk * nobs;
+                int kk = tid / nobs, o = tid - kk * nobs;
+                while (kk < N) {
+                    const int row = 4 * N + kk * nobs + o;
+                    if (!S.act[row]) {
+                        const double sl = (S.ex[o] * S.P[2 * (kk + 1)] + S.ey[o] * S.P[2 * (kk + 1) + 1] - S.hb[o]) * S.eni[o];
+                        if (sl < best) { best = sl; bid = row; }
+                    }
+                    kk += dk; o += dob;
+                    if (o >= nobs) { o -= nobs; ++kk; }
+                }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -246,6 +314,7 @@ __global__ void __launch_bounds__(T) mpc_long_kernel(StepConst C, int B, int N, 
                 sc.inner_done = 0;
             }
             __syncthreads();
+            PROF(3)
             if (sc.done) break;
 
             // ---- add row p: partial steps (dropping a row each) until the full step fits
@@ -267,57 +336,49 @@ __global__ void __launch_bounds__(T) mpc_long_kernel(StepConst C, int B, int N, 
                     S.d[j] = acc;
                 }
                 __syncthreads();
+                PROF(4)
+                // r = R^-1 d[0:q): 32-row diagonal blocks from the bottom up, each solved by warp 0 (long_tri32), the rows
+                // above a solved block updated by a thread-per-row product; the other warps form z = J[:, q:) d[q:)
+                // during the first triangle
+                for (int j = tid; j < q; j += T) S.r[j] = S.d[j];
+                bool z_done = false;
+                if (q > 0) __syncthreads();
+                for (int E = (q - 1) >> 5; E >= 0 && q > 0; --E) {
+                    const int lo = 32 * E, hi = min(q, lo + 32);
+                    if (warp == 0) {
+                        double me = lo + lane < hi ? S.r[lo + lane] : 0.0;
+                        me = long_tri32(S.R, S.rdi, n, lo, hi, lane, me);
+                        if (lo + lane < hi) S.r[lo + lane] = me;
+                    } else if (!z_done) {
+                        for (int i = tid - 32; i < n; i += T - 32) {
+                            const double* Ji = S.J + (size_t)i * ld;
+                            double acc = 0.0;
+                            for (int j = q; j < n; ++j) acc += Ji[j] * S.d[j];
+                            S.z[i] = acc;
+                        }
+                    }
+                    z_done = true;
+                    __syncthreads();
+                    if (E > 0) {
+                        for (int i = tid; i < lo; i += T) {
+                            const double* Ri = S.R + long_rbase(i, n);
+                            double acc = 0.0;
+                            for (int j = lo; j < hi; ++j) acc += Ri[j] * S.r[j];
+                            S.r[i] -= acc;
+                        }
+                        __syncthreads();
+                    }
+                }
+                PROF(11)
                 if (warp == 0) {
-                    // r = R^-1 d[0:q): column sweep in blocks of four columns; lane owns entries lane, lane+32, lane+64
-                    // (a solved entry stays in its owner's register as r_j).  Only the shuffles and the small 4x4
-                    // substitution are on the dependent chain; every shared-memory load is address-independent.
-                    double dl0 = lane < q ? S.d[lane] : 0.0;
-                    double dl1 = lane + 32 < q ? S.d[lane + 32] : 0.0;
-                    double dl2 = lane + 64 < q ? S.d[lane + 64] : 0.0;
-                    const int rb0 = long_rbase(lane, n), rb1 = long_rbase(lane + 32, n), rb2 = long_rbase(lane + 64, n);
-                    auto pick = [&](int j) {
-                        const int e = j >> 5;
-                        return __shfl_sync(0xffffffffu, e == 0 ? dl0 : (e == 1 ? dl1 : dl2), j & 31);
-                    };
-                    auto put = [&](int j, double v) {
-                        if (lane == (j & 31)) { const int e = j >> 5; if (e == 0) dl0 = v; else if (e == 1) dl1 = v; else dl2 = v; }
-                    };
-                    int j = q - 1;
-                    for (; j >= 3; j -= 4) {
-                        const double a0 = pick(j), a1 = pick(j - 1), a2 = pick(j - 2), a3 = pick(j - 3);
-                        const double* R1 = S.R + long_rbase(j - 1, n);
-                        const double* R2 = S.R + long_rbase(j - 2, n);
-                        const double* R3 = S.R + long_rbase(j - 3, n);
-                        const double r0 = a0 * S.rdi[j];
-                        const double r1 = (a1 - R1[j] * r0) * S.rdi[j - 1];
-                        const double r2 = (a2 - R2[j] * r0 - R2[j - 1] * r1) * S.rdi[j - 2];
-                        const double r3 = (a3 - R3[j] * r0 - R3[j - 1] * r1 - R3[j - 2] * r2) * S.rdi[j - 3];
-                        put(j, r0); put(j - 1, r1); put(j - 2, r2); put(j - 3, r3);
-                        if (lane < j - 3) { const double* Rr = S.R + rb0 + j; dl0 -= Rr[0] * r0 + Rr[-1] * r1 + Rr[-2] * r2 + Rr[-3] * r3; }
-                        if (lane + 32 < j - 3) { const double* Rr = S.R + rb1 + j; dl1 -= Rr[0] * r0 + Rr[-1] * r1 + Rr[-2] * r2 + Rr[-3] * r3; }
-                        if (lane + 64 < j - 3) { const double* Rr = S.R + rb2 + j; dl2 -= Rr[0] * r0 + Rr[-1] * r1 + Rr[-2] * r2 + Rr[-3] * r3; }
-                    }
-                    for (; j >= 0; --j) {
-                        const double rj = pick(j) * S.rdi[j];
-                        put(j, rj);
-                        if (lane < j) dl0 -= S.R[rb0 + j] * rj;
-                        if (lane + 32 < j) dl1 -= S.R[rb1 + j] * rj;
-                        if (lane + 64 < j) dl2 -= S.R[rb2 + j] * rj;
-                    }
-                    // dual step length t1 = min u_j / r_j over r_j > 0 (ties: lowest position)
+                    // dual step length t1 = min u_j / r_j over r_j > 0 (ties: lowest position), and |d[q:)|^2
                     const double rtol = 1e-13 * sqrt(sc.nn);
                     double t1 = INFINITY;
                     int l1 = INT_MAX;
-                    if (lane < q) { S.r[lane] = dl0; if (dl0 > rtol) { t1 = fmax(S.u[lane], 0.0) / dl0; l1 = lane; } }
-                    if (lane + 32 < q) {
-                        S.r[lane + 32] = dl1;
-                        if (dl1 > rtol) { const double v = fmax(S.u[lane + 32], 0.0) / dl1; if (v < t1) { t1 = v; l1 = lane + 32; } }
+                    for (int j = lane; j < q; j += 32) {
+                        const double rj = S.r[j];
+                        if (rj > rtol) { const double v = fmax(S.u[j], 0.0) / rj; if (v < t1) { t1 = v; l1 = j; } }
                     }
-                    if (lane + 64 < q) {
-                        S.r[lane + 64] = dl2;
-                        if (dl2 > rtol) { const double v = fmax(S.u[lane + 64], 0.0) / dl2; if (v < t1) { t1 = v; l1 = lane + 64; } }
-                    }
-                    // |d[q:)|^2
                     double acc = 0.0;
                     for (int jj = q + lane; jj < n; jj += 32) acc += S.d[jj] * S.d[jj];
 #pragma unroll
@@ -328,8 +389,7 @@ __global__ void __launch_bounds__(T) mpc_long_kernel(StepConst C, int B, int N, 
                         if (ov < t1 || (ov == t1 && oi < l1)) { t1 = ov; l1 = oi; }
                     }
                     if (lane == 0) { sc.d2n2 = acc; sc.t1 = t1; sc.l = l1 == INT_MAX ? -1 : l1; }
-                } else {
-                    // z = J[:, q:) d[q:)
+                } else if (!z_done) {
                     for (int i = tid - 32; i < n; i += T - 32) {
                         const double* Ji = S.J + (size_t)i * ld;
                         double acc = 0.0;
@@ -338,6 +398,7 @@ __global__ void __launch_bounds__(T) mpc_long_kernel(StepConst C, int B, int N, 
                     }
                 }
                 __syncthreads();
+                PROF(5)
                 if (tid == 0) {
                     const int it = ++sc.iters;
                     const double d2n2 = sc.d2n2;
@@ -356,6 +417,7 @@ __global__ void __launch_bounds__(T) mpc_long_kernel(StepConst C, int B, int N, 
                     }
                 }
                 __syncthreads();
+                PROF(6)
                 if (sc.inner_done) break;
                 const double t = sc.t;
                 const bool full = sc.full, dep = sc.dep;
@@ -386,6 +448,7 @@ __global__ void __launch_bounds__(T) mpc_long_kernel(StepConst C, int B, int N, 
                         sc.q = q + 1;
                     }
                     __syncthreads();
+                    PROF(7)
                     break;
                 }
                 // ---- partial step: row in position l leaves the active set
@@ -401,56 +464,58 @@ __global__ void __launch_bounds__(T) mpc_long_kernel(StepConst C, int B, int N, 
                     S.u[q - 1] = 0.0;
                 }
                 __syncthreads();
-                if (warp == 0) {
-                    // Rotations i = l..q-2 on rows (i, i+1) of R.  Lane owns columns l + lane + 32 e; the upper-row
-                    // entry of each owned column is carried in a register from one rotation to the next, the
-                    // lower-row entries are untouched until their rotation (loaded one rotation ahead), and the
-                    // pivot pair travels by shuffle: the dependent chain per rotation is shuffle -> rsqrt -> two FMAs.
-                    const int c0 = l + lane, c1 = c0 + 32, c2 = c0 + 64, qe = q - 1;
-                    const int rbl = long_rbase(l, n);
-                    double x0 = c0 < qe ? S.R[rbl + c0] : 0.0, x1 = c1 < qe ? S.R[rbl + c1] : 0.0, x2 = c2 < qe ? S.R[rbl + c2] : 0.0;
-                    int rbn = l + 1 < n ? long_rbase(l + 1, n) : 0;
-                    double y0 = (c0 < qe && l + 1 <= c0 + 1) ? S.R[rbn + c0] : 0.0;
-                    double y1 = (c1 < qe) ? S.R[rbn + c1] : 0.0;
-                    double y2 = (c2 < qe) ? S.R[rbn + c2] : 0.0;
-                    for (int i = l; i < qe; ++i) {
-                        const int rbi = long_rbase(i, n), rbi1 = rbn;
-                        // prefetch the lower row of the next rotation (row i+2), only where it is stored (c >= i+1)
-                        double yn0 = 0.0, yn1 = 0.0, yn2 = 0.0;
-                        if (i + 1 < qe) {
-                            rbn = long_rbase(i + 2, n);
-                            if (c0 < qe && c0 >= i + 1) yn0 = S.R[rbn + c0];
-                            if (c1 < qe && c1 >= i + 1) yn1 = S.R[rbn + c1];
-                            if (c2 < qe && c2 >= i + 1) yn2 = S.R[rbn + c2];
+                PROF(8)
+                // Rotations i = l..q-2 on rows (i, i+1) of R, in chunks of 32 pivot columns.  Inside a chunk warp 0 runs
+                // the wavefront: lane owns column cb + lane, the upper-row entry is carried in a register from one
+                // rotation to the next, the lower-row entry is loaded one rotation ahead, the pivot pair travels by
+                // shuffle (chain per rotation: shuffle -> rsqrt -> two FMAs).  Columns to the right of the chunk catch
+                // up afterwards, one thread per column, from the stored (c_i, s_i).
+                for (int cb = l; cb < q - 1; cb += 32) {
+                    const int qe = q - 1, ce = min(cb + 32, qe);
+                    if (warp == 0) {
+                        const int c = cb + lane;
+                        const bool own = c < ce;
+                        double x = own ? S.R[long_rbase(cb, n) + c] : 0.0;
+                        int rbi = long_rbase(cb, n), rbi1 = long_rbase(cb + 1, n);
+                        double y = own ? S.R[rbi1 + c] : 0.0;
+                        for (int i = cb; i < ce; ++i) {
+                            const int rbi2 = rbi1 + (n - i - 1);               // rbase(i+2)
+                            double yn = 0.0;
+                            if (own && c >= i + 1 && i + 2 <= qe) yn = S.R[rbi2 + c];
+                            const double a = __shfl_sync(0xffffffffu, x, i - cb);
+                            const double bb = __shfl_sync(0xffffffffu, y, i - cb);
+                            const double h2 = a * a + bb * bb;
+                            const double inv = h2 > 0.0 ? rsqrt_f64(h2) : 0.0;
+                            const double c_ = h2 > 0.0 ? a * inv : 1.0, s_ = bb * inv;
+                            if (own && c >= i) {
+                                S.R[rbi + c] = c_ * x + s_ * y;
+                                x = c_ * y - s_ * x;
+                                if (c == i) { S.R[rbi1 + c] = 0.0; S.cs[i] = c_; S.sn[i] = s_; S.rdi[i] = inv; }
+                            }
+                            y = yn;
+                            rbi = rbi1; rbi1 = rbi2;
                         }
-                        const int e = (i - l) >> 5, src = (i - l) & 31;
-                        const double a = __shfl_sync(0xffffffffu, e == 0 ? x0 : (e == 1 ? x1 : x2), src);
-                        const double bb = __shfl_sync(0xffffffffu, e == 0 ? y0 : (e == 1 ? y1 : y2), src);
-                        const double h2 = a * a + bb * bb;
-                        const double inv = h2 > 0.0 ? rsqrt_f64(h2) : 0.0;
-                        const double c_ = h2 > 0.0 ? a * inv : 1.0, s_ = bb * inv;
-                        if (c0 >= i && c0 < qe) {
-                            const double nx = c_ * x0 + s_ * y0;
-                            S.R[rbi + c0] = nx;
-                            if (c0 == i) { S.R[rbi1 + c0] = 0.0; S.cs[i] = c_; S.sn[i] = s_; S.rdi[i] = inv; }
-                            x0 = c_ * y0 - s_ * x0;
+                    }
+                    __syncthreads();
+                    if (ce < qe) {
+                        for (int c = ce + tid; c < qe; c += T) {
+                            int rbi = long_rbase(cb, n);
+                            double x = S.R[rbi + c];
+                            for (int i = cb; i < ce; ++i) {
+                                const int rb_next = rbi + (n - i);            // rbase(i+1)
+                                const double y = S.R[rb_next + c];
+                                const double c_ = S.cs[i], s_ = S.sn[i];
+                                S.R[rbi + c] = c_ * x + s_ * y;
+                                x = c_ * y - s_ * x;
+                                rbi = rb_next;
+                            }
+                            S.R[rbi + c] = x;
                         }
-                        if (c1 >= i && c1 < qe) {
-                            const double nx = c_ * x1 + s_ * y1;
-                            S.R[rbi + c1] = nx;
-                            if (c1 == i) { S.R[rbi1 + c1] = 0.0; S.cs[i] = c_; S.sn[i] = s_; S.rdi[i] = inv; }
-                            x1 = c_ * y1 - s_ * x1;
-                        }
-                        if (c2 >= i && c2 < qe) {
-                            const double nx = c_ * x2 + s_ * y2;
-                            S.R[rbi + c2] = nx;
-                            if (c2 == i) { S.R[rbi1 + c2] = 0.0; S.cs[i] = c_; S.sn[i] = s_; S.rdi[i] = inv; }
-                            x2 = c_ * y2 - s_ * x2;
-                        }
-                        y0 = yn0; y1 = yn1; y2 = yn2;
+                        __syncthreads();
                     }
                 }
                 __syncthreads();
+                PROF(9)
                 // the same rotations on the columns of J: each thread walks its row
                 for (int r0 = tid; r0 < n; r0 += T) {
                     double* Ji = S.J + (size_t)r0 * ld;
@@ -465,6 +530,7 @@ __global__ void __launch_bounds__(T) mpc_long_kernel(StepConst C, int B, int N, 
                 }
                 if (tid == 0) sc.q = q - 1;
                 __syncthreads();
+                PROF(10)
             }
             __syncthreads();
         }
@@ -509,26 +575,39 @@ __global__ void __launch_bounds__(T) mpc_long_kernel(StepConst C, int B, int N, 
             }
         }
     }
+    PROF_FLUSH
 }
 
-template <int T>
+template <int T, int MINB>
 static int launch_long(const StepConst& C, int B, int N, int max_obs, const StepIO& io, cudaStream_t st) {
     const size_t smem = long_carve(N, max_obs, nullptr, nullptr);
     if (smem > 227 * 1024) return LDCBF_E_SHAPE;
-    auto kern = mpc_long_kernel<T>;
+    auto kern = mpc_long_kernel<T, MINB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_last_error(e); return LDCBF_E_LAUNCH; }
     int per_sm = (int)((227 * 1024) / (smem + 1024));
-    per_sm = per_sm < 1 ? 1 : (per_sm > 2048 / T ? 2048 / T : per_sm);
+    per_sm = per_sm < 1 ? 1 : (per_sm > MINB ? MINB : per_sm);
     const int grid = B < 148 * per_sm ? B : 148 * per_sm;
     const int iter_cap = C.max_iter * ((N + 3) / 4);
     kern<<<grid, T, smem, st>>>(C, B, N, max_obs, iter_cap, io);
     return check_launch();
 }
 
+#ifdef LDCBF_LONG_PROFILE
+extern "C" void ldcbf_debug_long_profile(unsigned long long* out12, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out12, g_long_prof, 12 * sizeof(unsigned long long));
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_long_prof, z, sizeof(z)); }
+}
+#endif
+
 int launch_long_horizon(const StepConst& C, int B, int N, int max_obs, const StepIO& io, cudaStream_t st) {
     if (N > LDCBF_MAX_HORIZON_LONG) return LDCBF_E_SHAPE;
-    return 2 * N <= 32 ? launch_long<64>(C, B, N, max_obs, io, st) : launch_long<128>(C, B, N, max_obs, io, st);
+    // block width and register budget by problem size: 2N <= 32 unknowns -> 64 threads, 8 blocks/SM (128 registers);
+    // 2N <= 64 -> 128 threads, 4 blocks/SM (128 registers); larger -> 128 threads, 2 blocks/SM (shared-memory bound)
+    if (2 * N <= 32) return launch_long<64, 8>(C, B, N, max_obs, io, st);
+    if (2 * N <= 64) return launch_long<128, 4>(C, B, N, max_obs, io, st);
+    return launch_long<128, 2>(C, B, N, max_obs, io, st);
 }
 
 }  // namespace ldcbf
