@@ -288,6 +288,7 @@ def run_ours(args):
             line["unknown_env"] = unknown_env_bench(L, flush, torch)
             line["latency_b1"] = latency_b1(L, torch)
             line["bounds_tuning"] = bounds_tuning_bench(torch)
+            line["long_horizon"] = long_horizon_bench(L, torch)
     if rank == 0:
         line["clocks"] = clk.summary()
         if port is not None:
@@ -484,6 +485,37 @@ def latency_b1(L, torch, n=200):
             tw.append((time.perf_counter() - t0) * 1e6)
     return {"p50_device_us": statistics.median(ts), "p50_wall_us": statistics.median(tw),
             "note": "B=1, config 1 step 0; reference: CasADi/IPOPT per step, not measurable offline"}
+
+
+def long_horizon_bench(L, torch):
+    """Config 5 (scaling sweep) samples: one open-loop MPC step per scenario at horizon 10 / 20 / 40 with 8 / 16 / 64
+    octagonal obstacles, solved by the block-per-scenario kernel (csrc/mpc_long.cu)."""
+    from ldcbf_b200 import scenarios
+    cu = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).cuda()
+    prm = L.default_params(0.4)
+    rows = []
+    for N, n_obs, B in ((10, 8, 8192), (20, 16, 4096), (40, 64, 1184)):
+        sc = scenarios.config5(B, n_obs, seed=0)
+        foots = scenarios.foot_window(sc["right_first"], 0, N)
+        args = (prm, cu(sc["state"][:, :4]), cu(sc["state"][:, 4]), cu(sc["goal"]), cu(foots, torch.int8),
+                cu(sc["verts"]), cu(sc["nverts"], torch.int32), cu(sc["nobs"], torch.int32))
+        out = L.mpc_step(*args)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = L.mpc_step(*args, out=out)
+            e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = statistics.median(ts)
+        st = out["status"]
+        rows.append({"horizon": N, "obstacles": n_obs, "batch": B, "ms": ms, "value": B / (ms * 1e-3), "unit": UNIT,
+                     "solved": int((st == 0).sum().item()), "infeasible": int((st == 2).sum().item()),
+                     "iteration_cap": int((st == 1).sum().item()),
+                     "mean_iterations": float(out["iters"].double().mean().item())})
+    return rows
 
 
 def bounds_tuning_bench(torch):
