@@ -289,6 +289,7 @@ def run_ours(args):
             line["latency_b1"] = latency_b1(L, torch)
             line["bounds_tuning"] = bounds_tuning_bench(torch)
             line["long_horizon"] = long_horizon_bench(L, torch)
+            line["clearance_grid"] = clearance_bench(L, torch)
     if rank == 0:
         line["clocks"] = clk.summary()
         if port is not None:
@@ -516,6 +517,32 @@ def long_horizon_bench(L, torch):
                      "iteration_cap": int((st == 1).sum().item()),
                      "mean_iterations": float(out["iters"].double().mean().item())})
     return rows
+
+
+def clearance_bench(L, torch, B=1024):
+    """f3: occupancy grid + exact distance transform + clearance cost of the sub-goal planner's front-end
+    (HumanoidMPCWithRRT.py:21-88,103-108) for B jittered copies of the config-4 wall map, 251 x 274 cells each."""
+    from ldcbf_b200 import scenarios
+    rng = np.random.default_rng(0)
+    wall = np.array([[2.0, -3.0], [3.0, -3.0], [3.0, 3.0], [2.0, 3.0]])
+    rings = [[wall + rng.uniform(-0.2, 0.2, 2)] for _ in range(B)]
+    verts, nverts, nobs = scenarios.pack_rings(rings)
+    cu = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).cuda()
+    args = (cu(np.tile([5.0, 0.0], (B, 1))), cu(verts), cu(nverts, torch.int32), cu(nobs, torch.int32))
+    r = L.clearance_grid(*args, h_cap=288)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = L.clearance_grid(*args, h_cap=288)
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = statistics.median(ts)
+    cells = float((r["meta"][:, 4] + 1).sum().item()) * 251
+    return {"batch": B, "ms": ms, "value": B / (ms * 1e-3), "unit": "maps/s", "cells_per_s": cells / (ms * 1e-3),
+            "note": "timed through the binding: includes the output allocations (zero-filled) of the call"}
 
 
 def bounds_tuning_bench(torch):

@@ -1,8 +1,12 @@
-"""Mirror of the sub-goal sequencing of `MPC/HumanoidMPCVariants/HumanoidMPCWithRRT.py:153-181`.
+"""Mirror of `MPC/HumanoidMPCVariants/HumanoidMPCWithRRT.py`.
 
-The occupancy grid, clearance cost and RRT* planning (reference :21-135, third-party `rrtplanner==0.1.2`) are out
-of scope: the way-points are an input.  The sequencing itself — a fresh MPC per sub-goal,
-state carried over, foot parity restarted, start hard-coded to the origin (:155) — runs inside one rollout launch.
+* `_build_occupancy_grid` (:21-88) and the clearance cost (:103-108) run on the GPU (`ldcbf_clearance_grid_f64`,
+  bit-exact grid and distances).
+* The RRT* search (:110-135) is the third-party `rrtplanner==0.1.2` in the reference, absent offline: `rrt_star.py` is an
+  independent host implementation with the same parameters and edge cost; its random tree is not the reference's
+  (parity unpinned).  Way-points can also be passed in directly as `sub_goals=[...]`.
+* The sequencing (:153-181) — a fresh MPC per sub-goal, state carried over, foot parity restarted, start hard-coded
+  to the origin (:155) — runs inside one rollout launch.
 """
 import numpy as np
 import torch
@@ -13,12 +17,50 @@ from HumanoidNavigation.Utils.ObstaclesUtils import hull_ring
 
 
 class HumanoidMPCWithRRT(HumanoidMPC):
+    def _clearance(self, width_grid_size):
+        from ldcbf_b200.scenarios import pack_rings
+        t = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=self._dev)
+        verts, nverts, nobs = pack_rings([[hull_ring(o) for o in self.obstacles]])
+        r = ldcbf_b200.clearance_grid(t(np.asarray(self.goal, dtype=np.float64)[None, :]), t(verts),
+                                      t(nverts, torch.int32), t(nobs, torch.int32), width=width_grid_size)
+        min_x, min_y, max_x, max_y, height, _ = r["meta"][0].cpu().numpy()
+        height = int(height)
+        cut = lambda a: a[0, :, :height + 1].cpu().numpy()
+        return cut(r["og"]).astype(np.float64), cut(r["dist"]), cut(r["cost"]), (min_x, min_y, max_x, max_y, height)
+
+    def _build_occupancy_grid(self, width_grid_size: int):
+        """(occupancy_grid[width+1, height+1], world -> grid, grid -> world) like the reference (:21-88)."""
+        og, _, _, (min_x, min_y, max_x, max_y, height) = self._clearance(width_grid_size)
+        fwd = lambda x_glob, y_glob: np.array([                                                     # :55-58
+            np.round(((x_glob - min_x) / (max_x - min_x)) * width_grid_size),
+            np.round(((y_glob - min_y) / (max_y - min_y)) * height),
+        ]).astype(int)
+        inv = lambda x_og, y_og: np.array([                                                         # :60-63
+            min_x + ((x_og * (max_x - min_x)) / width_grid_size),
+            min_y + ((y_og * (max_y - min_y)) / height),
+        ])
+        return og, fwd, inv
+
+    def plan_sub_goals(self, width_grid_size=250, n=1500, r_rewire=80, seed=1, shortcut=True):
+        """Way-points from the start (0,0) to the goal (:97-135): GPU map + clearance cost, host RRT*
+        (+ a cost-non-increasing shortcut pass, see rrt_star.RRTStar.shortcut)."""
+        from HumanoidNavigation.MPC.HumanoidMPCVariants.rrt_star import RRTStar
+        og, fwd, inv = self._build_occupancy_grid(width_grid_size)
+        _, _, costs, _ = self._clearance(width_grid_size)
+        planner = RRTStar(og, costs, n=n, r_rewire=r_rewire, seed=seed)
+        path = planner.plan(fwd(0, 0), fwd(self.goal[0], self.goal[1]))
+        if path is None:
+            raise RuntimeError("RRT*: no collision-free path found")
+        if shortcut:
+            path = planner.shortcut(path)
+        return np.array([inv(p[0], p[1]) for p in path[1:]])                                       # edge end points, :131-135
+
     def run_simulation(self, path_to_gif: str = None, make_fast_plot: bool = True, plot_animation: bool = False,
                        fill_animator: bool = True, initial_animator=None, visualize_rrt_path: bool = False,
                        path_to_rrt_pdf: str = None, sub_goals=None):
         if sub_goals is None:
-            raise NotImplementedError("RRT* planning is out of scope here (rrtplanner is a third-party dependency of "
-                                      "the reference); pass the way-points as sub_goals=[(x, y), ...]")
+            sub_goals = self.plan_sub_goals()
+        self.sub_goals = np.asarray(sub_goals, dtype=np.float64)
         from ldcbf_b200.scenarios import pack_rings
         t = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=self._dev)
         goals = np.asarray(sub_goals, dtype=np.float64).reshape(1, -1, 2)

@@ -3,9 +3,10 @@
 There is no CPU fallback: importing the solver entry points without the built library raises, and every call
 requires CUDA tensors.  Build with `python __graft_entry__.py build` (or `make -C .../csrc`).
 """
-from .binding import (LdcbfParams, Status, abi_version, default_params, half_planes, lib, lidar_cast, lidar_clusters, mpc_qp,
+from .binding import (LdcbfParams, Status, abi_version, clearance_grid, default_params, half_planes, lib, lidar_cast,
+                      lidar_clusters, mpc_qp,
                       mpc_step, mpc_step_packed, params_from_conf, probe_fp64, rollout)
 from .batched import BatchedHumanoidMPC, BatchedUnknownEnvMPC
 
-__all__ = ["LdcbfParams", "Status", "abi_version", "default_params", "half_planes", "lib", "lidar_cast", "lidar_clusters", "mpc_qp",
+__all__ = ["LdcbfParams", "Status", "abi_version", "clearance_grid", "default_params", "half_planes", "lib", "lidar_cast", "lidar_clusters", "mpc_qp",
            "mpc_step", "mpc_step_packed", "params_from_conf", "probe_fp64", "rollout", "BatchedHumanoidMPC", "BatchedUnknownEnvMPC"]

@@ -16,7 +16,7 @@ MAX_HORIZON_LONG = 48  # LDCBF_MAX_HORIZON_LONG: block-per-scenario solver for 5
 EXPORTS = ("ldcbf_abi_version", "ldcbf_params_default", "ldcbf_last_cuda_error", "ldcbf_workspace_bytes",
            "ldcbf_halfplanes_f64", "ldcbf_mpc_qp_f64", "ldcbf_mpc_step_f64", "ldcbf_mpc_step_packed_f64",
            "ldcbf_lidar_cast_f64",
-           "ldcbf_lidar_clusters_f64",
+           "ldcbf_lidar_clusters_f64", "ldcbf_clearance_grid_f64",
            "ldcbf_rollout_f64", "ldcbf_probe_fp64_fma")
 
 
@@ -61,6 +61,7 @@ def lib():
         L.ldcbf_mpc_step_packed_f64.argtypes = [POINTER(LdcbfParams), c_int, c_int, c_int, c_int] + [P] * 11
         L.ldcbf_lidar_cast_f64.argtypes = [c_int, c_int, P, c_double, P, c_int, c_int, P, P, P, P, P, P, P]
         L.ldcbf_lidar_clusters_f64.argtypes = [c_int, c_int, P, P, c_double, c_int, c_int, c_int, P, P, P, P, P, P]
+        L.ldcbf_clearance_grid_f64.argtypes = [c_int, c_int, c_int, c_int, c_int] + [P] * 10
         L.ldcbf_rollout_f64.argtypes = [POINTER(LdcbfParams)] + [c_int] * 7 + [P] * 15
         L.ldcbf_probe_fp64_fma.argtypes = [c_int, c_int, c_int, P, P]
         for name in EXPORTS:
@@ -226,6 +227,31 @@ def lidar_cast(pos, verts, nverts, nobs, lidar_range, resolution=360, rays=None)
                                           _ptr(hit_obs[s:e], I32, "hit_obs"), _ptr(hit_edge[s:e], I32, "hit_edge"),
                                           _ptr(hit_xy[s:e], F64, "hit_xy"), _stream()), "ldcbf_lidar_cast_f64")
     return hit_obs, hit_edge, hit_xy
+
+
+def clearance_grid(goal, verts, nverts, nobs, width=250, h_cap=None, with_cost=True):
+    """f3: occupancy grid + exact distance transform + clearance cost of the planner front-end
+    (HumanoidMPCWithRRT.py:21-88,103-108) for a batch of maps.
+    Returns dict(meta[B,6] = (min_x, min_y, max_x, max_y, height, occupied cells), og[B,width+1,h_cap+1] uint8,
+    dist, cost[B,width+1,h_cap+1] fp64); cells with j > height are zero.  `h_cap` defaults to 2*width (a frame at
+    most twice as tall as wide); a map that needs more raises."""
+    B = goal.shape[0]
+    h_cap = int(h_cap) if h_cap is not None else 2 * int(width)
+    dev = goal.device
+    shape = (B, int(width) + 1, h_cap + 1)
+    out = dict(meta=torch.zeros((B, 6), dtype=F64, device=dev), og=torch.zeros(shape, dtype=torch.uint8, device=dev),
+               dist=torch.zeros(shape, dtype=F64, device=dev),
+               cost=torch.zeros(shape, dtype=F64, device=dev) if with_cost else None)
+    work = torch.empty(shape, dtype=I32, device=dev)
+    _check(lib().ldcbf_clearance_grid_f64(B, int(width), h_cap, verts.shape[1], verts.shape[2], _ptr(goal, F64, "goal"),
+                                          _ptr(verts, F64, "verts"), _ptr(nverts, I32, "nverts"),
+                                          _ptr(nobs, I32, "nobs"), _ptr(out["meta"], F64, "meta"),
+                                          _ptr(out["og"], torch.uint8, "og"), _ptr(out["dist"], F64, "dist"),
+                                          _ptr(out["cost"], F64, "cost"), _ptr(work, I32, "work"), _stream()),
+           "ldcbf_clearance_grid_f64")
+    if bool((out["meta"][:, 5] < 0).any()):
+        raise ValueError("ldcbf_clearance_grid_f64: a map needs more than h_cap grid rows (or has no obstacle)")
+    return out
 
 
 def lidar_clusters(hit_xy, noise=None, eps=0.3, min_samples=3, max_hulls=MAX_OBSTACLES, max_hull_verts=16):

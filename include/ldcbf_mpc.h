@@ -159,6 +159,22 @@ int ldcbf_lidar_clusters_f64(int B, int R, const double* hit_xy, const double* n
                              int max_hulls, int max_hull_verts, int32_t* labels, double* hull_verts,
                              int32_t* hull_nverts, int32_t* n_hulls, int32_t* overflow, void* cuda_stream);
 
+/* f3 — map front-end of the sub-goal planner: occupancy grid, exact Euclidean distance transform and clearance
+ * cost, batched.  Replaces HumanoidMPCWithRRT.py:21-88 (_build_occupancy_grid: frame = bounding box of the hull
+ * vertices, the origin and the goal padded by 3; height = ceil(width * dy / dx); np.round to cells; cells of
+ * [xmin,xmax) x [ymin,ymax) inside the triangulated rounded hull) and :103-108 (scipy distance_transform_edt(1 - og),
+ * exp(-d)).  The RRT* search that consumes the cost map lives in the un-vendored rrtplanner package and stays on
+ * the host (mirror: HumanoidNavigation/MPC/HumanoidMPCVariants/rrt_star.py).
+ *   goal [B,2]; verts/nverts/nobs as in K1 (hull rings)
+ *   meta [B,6] out = (min_x, min_y, max_x, max_y, height_grid_size, occupied cells or -1 when height > h_cap)
+ *   og   [B,width+1,h_cap+1] uint8 out (cell (i,j), j fastest; columns above height_grid_size are zero)
+ *   dist, cost [B,width+1,h_cap+1] out (cost may be NULL); entries with j > height_grid_size are not written
+ *   work [B,width+1,h_cap+1] int32 scratch
+ * og and dist are bit-exact against the reference; cost within 1 ulp of np.exp. */
+int ldcbf_clearance_grid_f64(int B, int width, int h_cap, int max_obs, int max_verts, const double* goal,
+                             const double* verts, const int32_t* nverts, const int32_t* nobs, double* meta,
+                             uint8_t* og, double* dist, double* cost, int32_t* work, void* cuda_stream);
+
 /* Closed loop (HumanoidMpc.py:380-459, incl. the mpc_step = int(DELTA_T/sampling_time) sub-stepping of :74-78,
  * :384,:443-446) with optional sub-goal sequencing (HumanoidMPCVariants/HumanoidMPCWithRRT.py:153-181: a fresh
  * run per sub-goal — objective memory and foot parity restart, the state carries over).  One kernel launch.
