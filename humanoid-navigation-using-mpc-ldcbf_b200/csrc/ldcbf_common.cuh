@@ -23,6 +23,8 @@ struct StepConst {
     double foot_offset, stop_objective, sampling_time;
     double eps_active, eps_const_row;
     int max_iter;
+    bool cold_start;      // LDCBF_FLAG_COLD_START: no initial active-set guess / no warm start
+    bool coop_lanes;      // LDCBF_FLAG_COOP_LANES: warp-per-scenario solver for small batches (N <= 3, <= 8 obstacles)
 };
 
 inline StepConst make_const(const ldcbf_params& p) {
@@ -44,6 +46,8 @@ inline StepConst make_const(const ldcbf_params& p) {
     c.foot_offset = p.foot_offset; c.stop_objective = p.stop_objective; c.sampling_time = p.sampling_time;
     c.eps_active = p.eps_active; c.eps_const_row = p.eps_const_row;
     c.max_iter = p.max_iter;
+    c.cold_start = (p.flags & LDCBF_FLAG_COLD_START) != 0;
+    c.coop_lanes = (p.flags & LDCBF_FLAG_COOP_LANES) != 0;
     return c;
 }
 

@@ -443,6 +443,24 @@ LDCBF_HD void qp_trip(const StepConst& C, double* ws, QpState<N, MO>& s) {
     }
 }
 
+// Initial active-set guess for a solve with no history (open-loop batches, first step of a loop): all 2N velocity
+// rows, each on the side the goal lies on (r . (goal - p_0) > 0 -> upper bound).  Measured on config 2 (4096
+// scenarios): the optimum is a vertex with ~6 active rows, three quarters of them velocity rows, and the cold start from
+// the unconstrained optimum wanders (adds late-stage rows first, drops them again); this guess, repaired by
+// qp_warm_start, replaces 14.8 trips per solve by 5.1 with identical results.  Any guess is safe: qp_warm_start
+// keeps the method exact.  LDCBF_FLAG_COLD_START disables it.
+template <int N, int MO>
+LDCBF_HD void guess_codes(const QpState<N, MO>& s, int (&codes)[2 * N]) {
+    const double dgx = s.gx - s.p0x, dgy = s.gy - s.p0y;
+#pragma unroll
+    for (int k = 1; k <= N; ++k) {
+        const double lon = s.rc[k] * dgx + s.rs[k] * dgy;
+        const double lat = (double)s.ft[k] * s.rc[k] * dgy - s.rs[k] * dgx;
+        codes[2 * (k - 1)] = 2 * (2 * N + 2 * (k - 1)) + (lon > 0.0 ? 1 : 0);
+        codes[2 * (k - 1) + 1] = 2 * (2 * N + 2 * (k - 1) + 1) + (lat > 0.0 ? 1 : 0);
+    }
+}
+
 // Warm start of the dual active-set method from a guessed active set (closed loop: the final active set of the
 // previous MPC step shifted by one stage, `shift_codes`).  Goldfarb-Idnani may start from any point that is the
 // optimum of the equality-constrained problem on a set of independent rows with non-negative multipliers, so:
@@ -511,6 +529,7 @@ LDCBF_HD void qp_warm_start(const StepConst& C, const int (&codes)[2 * N], doubl
     bool fail = false;
     double uu[NV];
     for (int round = 0; round <= NV; ++round) {
+        ++s.iters;      // a round costs about one trip (Gram matrix, Cholesky, two solves) and is counted as one
         // Gram matrix of the loaded slots (identity on the empty ones), Cholesky, u = G^-1 rhs
         double L[NV][NV];
 #pragma unroll
@@ -662,6 +681,11 @@ LDCBF_HD void solve_scenario(const StepConst& C, double p0x, double v0x, double 
                              int n_stream, double delta, const Limits& lim, double* ws, QpSolution<N>& S) {
     QpState<N, MO> s;
     qp_setup<N, MO, WS>(C, p0x, v0x, p0y, v0y, th0, gx, gy, ft, ce, nb, ce_stream, n_stream, delta, lim, ws, s);
+    if (!C.cold_start) {
+        int codes[2 * N];
+        guess_codes<N, MO>(s, codes);
+        qp_warm_start<N, MO, WS>(C, codes, ws, s);
+    }
     while (!s.done) qp_trip<N, MO, WS>(C, ws, s);
     qp_finish<N, MO>(C, s, S);
 }

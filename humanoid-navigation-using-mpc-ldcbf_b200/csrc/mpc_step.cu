@@ -2,14 +2,21 @@
 // See mpc_qp.cuh for the formulation and the reference lines each piece replaces.
 #include <mutex>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "mpc_qp.cuh"
+#include "mpc_qp_coop.cuh"
 #include "step_io.cuh"
 
 #ifndef LDCBF_QP_REFILL_TRIPS
 #define LDCBF_QP_REFILL_TRIPS 1
 #endif
+// lanes that must be free before a warp stops to retire / refill them.  With the initial active-set guess the fixed
+// work per scenario (setup + warm start, done inside the divergent refill region) outweighs the trips, so the
+// region should run as full as possible: measured at B = 2^20, 8 -> 2.31 ms, 16 -> 1.80, 24 -> 1.63, 32 -> 1.99.
 #ifndef LDCBF_QP_REFILL_MIN_IDLE
-#define LDCBF_QP_REFILL_MIN_IDLE 8
+#define LDCBF_QP_REFILL_MIN_IDLE 24
 #endif
 
 namespace ldcbf {
@@ -137,6 +144,11 @@ __global__ void __launch_bounds__(BLOCK) mpc_qp_refill_kernel(StepConst C, int B
                     for (int o = 0; o < MO; ++o) ce[o] = (o < nb) ? gce[o] : make_double4(0.0, 0.0, 0.0, 0.0);
                     qp_setup<N, MO, BLOCK>(C, x.x, x.y, x.z, x.w, th0, g.x, g.y, ft, ce, nb, gce + MO, nt - nb,
                                            io.delta ? io.delta[b] : 0.0, lim, ws, s);
+                    if (!C.cold_start) {
+                        int codes[2 * N];
+                        guess_codes<N, MO>(s, codes);
+                        qp_warm_start<N, MO, BLOCK>(C, codes, ws, s);
+                    }
                 }
                 next = min(end, next + __popc(free_m));
             }
@@ -147,6 +159,52 @@ __global__ void __launch_bounds__(BLOCK) mpc_qp_refill_kernel(StepConst C, int B
             if (b >= 0 && !s.done) qp_trip<N, MO, BLOCK>(C, ws, s);
         }
     }
+}
+
+// Batches that do not fill the GPU: G lanes per scenario (mpc_qp_coop.cuh).  BLOCK / G scenarios per block, each with
+// its own slice of shared memory; a group whose scenario index is past the batch leaves at once.
+template <int N, int MO, int G, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) mpc_qp_coop_kernel(StepConst C, int B, int max_obs, StepIO io) {
+    extern __shared__ double qp_ws[];
+    const int gi = threadIdx.x / G;
+    const int b = blockIdx.x * (BLOCK / G) + gi;
+    if (b >= B) return;
+    LaneGroup<G> grp;
+    grp.lane = threadIdx.x % G;
+    grp.mask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) / G * G));
+    double4 x;
+    double th0;
+    load_state(io, b, x, th0);
+    const double2 g = reinterpret_cast<const double2*>(io.goal)[b];
+    int ft[N + 1];
+    load_foot<N>(io, b, ft);
+    const Limits lim = load_limits(C, io.limits, (size_t)b);
+    const int nobs = min(min(io.nobs[b], max_obs), MO);
+    const double4* gce = reinterpret_cast<const double4*>(io.c_eta) + (size_t)b * max_obs;
+    QpSolution<N> S;
+    coop_solve_scenario<N, MO, G>(C, grp, x.x, x.y, x.z, x.w, th0, g.x, g.y, ft, gce, nobs,
+                                  io.delta ? io.delta[b] : 0.0, lim, qp_ws + (size_t)gi * CoopShape<N, MO>::DOUBLES, S);
+    if (grp.lane == 0) store_solution<N>(S, b, io);
+}
+
+template <int N, int MO, int G, int BLOCK>
+static int launch_qp_coop(const StepConst& C, int B, int max_obs, const StepIO& io, cudaStream_t st) {
+    constexpr int PER_BLOCK = BLOCK / G;
+    const size_t smem = (size_t)CoopShape<N, MO>::DOUBLES * sizeof(double) * PER_BLOCK;
+    auto kern = mpc_qp_coop_kernel<N, MO, G, BLOCK>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_last_error(e); return LDCBF_E_LAUNCH; }
+    }
+    kern<<<(unsigned)((B + PER_BLOCK - 1) / PER_BLOCK), BLOCK, smem, st>>>(C, B, max_obs, io);
+    return check_launch();
+}
+
+// development aid: LDCBF_COOP_MAX_B overrides the largest batch routed to the cooperative kernel, LDCBF_COOP_G the
+// lanes per scenario (8, 16 or 32)
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
 }
 
 template <int N, int MO, int BLOCK>
@@ -166,6 +224,20 @@ static int launch_qp(const StepConst& C, int B, int max_obs, const StepIO& io, c
     // Large batches: 128-thread blocks.  Small batches leave SM sub-partitions idle, so the scenarios are spread
     // over more, narrower warps (8 lanes used per warp): a warp runs until its slowest lane has converged, and the
     // expected maximum iteration count over 8 scenarios is well below that over 32.
+    // Opt-in (LDCBF_FLAG_COOP_LANES): a whole warp per scenario with the QR-updated solver of mpc_qp_coop.cuh.
+    // Measured (cold start on both sides): 25-35 % faster than one thread per scenario for 64 <= B <= 1024 (B = 512:
+    // 61 -> 41 us), equal at B = 4096 with 8 lanes per scenario, slower beyond; no named configuration falls in its
+    // range and it has no initial guess yet, so it is not the default.
+    if constexpr (N <= 3) {
+        static const int coop_max_b = env_int("LDCBF_COOP_MAX_B", 1024);
+        static const int coop_g = env_int("LDCBF_COOP_G", 0);
+        if (C.coop_lanes && max_obs <= MO && B <= coop_max_b) {
+            const int g = coop_g ? coop_g : 32;
+            if (g == 32) return launch_qp_coop<N, MO, 32, 32>(C, B, max_obs, io, st);
+            if (g == 16) return launch_qp_coop<N, MO, 16, 32>(C, B, max_obs, io, st);
+            return launch_qp_coop<N, MO, 8, 32>(C, B, max_obs, io, st);
+        }
+    }
     if (B >= 148 * 2 * 128 * 4) {
         // persistent grid: 2 blocks of 128 threads per SM (register-limited occupancy), >= 128 scenarios per warp
         constexpr int BLOCK = 128, TRIPS = LDCBF_QP_REFILL_TRIPS;

@@ -77,7 +77,13 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
                 QpState<N, MO> qs;
                 double* ws = qp_ws + threadIdx.x;
                 qp_setup<N, MO, BLOCK>(C, px, vx, py, vy, th, gx, gy, ft, ce, nb, nullptr, 0, dl, lim, ws, qs);
-                if (io.warm_start) qp_warm_start<N, MO, BLOCK>(C, warm, ws, qs);
+                if (io.warm_start) {
+                    bool any = false;                       // nothing carried over (first step of a run): geometric guess
+#pragma unroll
+                    for (int j = 0; j < 2 * N; ++j) any |= warm[j] >= 0;
+                    if (!any) guess_codes<N, MO>(qs, warm);
+                    qp_warm_start<N, MO, BLOCK>(C, warm, ws, qs);
+                }
                 while (!qs.done) qp_trip<N, MO, BLOCK>(C, ws, qs);
                 qp_finish<N, MO>(C, qs, S);
                 shift_codes<N, MO, BLOCK>(qs, ws, warm);

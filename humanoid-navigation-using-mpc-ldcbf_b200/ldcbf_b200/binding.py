@@ -31,6 +31,7 @@ class LdcbfParams(ctypes.Structure):
 
 FLAG_FAST_GEOMETRY = 1
 FLAG_COLD_START = 2
+FLAG_COOP_LANES = 4
 
 
 class Status:

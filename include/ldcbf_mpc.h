@@ -77,6 +77,12 @@ typedef struct ldcbf_params {
 /* ldcbf_rollout_f64 warm-starts every solve from the previous step's active set shifted by one stage (the result is
  * exact either way; the reference warm-starts IPOPT the same way, HumanoidMpc.py:450-455).  COLD_START disables it. */
 #define LDCBF_FLAG_COLD_START 2
+/* The open-loop entry points (ldcbf_mpc_qp_f64, ldcbf_mpc_step_f64, ldcbf_mpc_step_packed_f64) start every solve
+ * from a geometric active-set guess (all velocity rows on the side the goal lies on) instead of the empty set: same
+ * optimum, about a third of the iterations.  COLD_START disables that as well.
+ * COOP_LANES: batches of at most 1024 scenarios with N <= 3 and at most 8 obstacles are solved by one warp per
+ * scenario (QR-updated active set, rows scanned in parallel) instead of one thread per scenario. */
+#define LDCBF_FLAG_COOP_LANES 4
 
 /* Optional per-scenario overrides of the limits `bounds_tuning.py:22-26` mutates:
  * limits[b] = (ALPHA, V_MAX[0], V_MAX[1], OMEGA_MAX, OMEGA_MIN, reserved).  NaN entries fall back to ldcbf_params. */

@@ -23,6 +23,7 @@ extern "C" int qp_host_solve_n3_warm(const ldcbf_params* prm, int max_obs, const
                        load_limits(C, nullptr, 0), ws, s);
     int codes[2 * N];
     for (int j = 0; j < 2 * N; ++j) codes[j] = codes_in[j];
+    if (codes_in[0] == -2) guess_codes<N, MO>(s, codes);      // -2: the kernel's own initial guess
     qp_warm_start<N, MO, 1>(C, codes, ws, s);
     while (!s.done) qp_trip<N, MO, 1>(C, ws, s);
     QpSolution<N> S;
@@ -68,4 +69,107 @@ extern "C" int qp_host_solve_n3(const ldcbf_params* prm, int B, int max_obs, con
         obj[b] = S.obj; status[b] = S.status; iters[b] = S.iters;
     }
     return 0;
+}
+
+// Cooperative variant (csrc/mpc_qp_coop.cuh) with a group of one lane: same QR-updated active-set code as the GPU
+// kernel, the group collectives reduce to the identity.
+#include "mpc_qp_coop.cuh"
+
+template <int N, int MO>
+static void coop_host_batch(const ldcbf_params* prm, int B, int max_obs, const double* x0, const double* theta0,
+                            const double* goal, const int8_t* foot, const double* c_eta, const int32_t* nobs,
+                            const double* delta, double* U, double* X, double* theta, double* omega, double* obj,
+                            int32_t* status, int32_t* iters) {
+    using namespace ldcbf;
+    const StepConst C = make_const(*prm);
+    LaneGroup<1> grp{1u, 0};
+    for (int b = 0; b < B; ++b) {
+        int ft[N + 1];
+        for (int k = 0; k <= N; ++k) ft[k] = foot[b * (N + 1) + k];
+        const int nb = nobs[b] < MO ? nobs[b] : MO;
+        QpSolution<N> S;
+        double sm[CoopShape<N, MO>::DOUBLES];
+        coop_solve_scenario<N, MO, 1>(C, grp, x0[4 * b], x0[4 * b + 1], x0[4 * b + 2], x0[4 * b + 3], theta0[b],
+                                      goal[2 * b], goal[2 * b + 1], ft,
+                                      reinterpret_cast<const double4*>(c_eta + (size_t)b * max_obs * 4), nb,
+                                      delta ? delta[b] : 0.0, load_limits(C, nullptr, 0), sm, S);
+        for (int k = 0; k < N; ++k) { U[(b * N + k) * 2] = S.ux[k]; U[(b * N + k) * 2 + 1] = S.uy[k]; omega[b * N + k] = S.om[k]; }
+        for (int k = 0; k <= N; ++k) {
+            double* x = X + ((size_t)b * (N + 1) + k) * 4;
+            x[0] = S.px[k]; x[1] = S.vx[k]; x[2] = S.py[k]; x[3] = S.vy[k];
+            theta[b * (N + 1) + k] = S.th[k];
+        }
+        obj[b] = S.obj; status[b] = S.status; iters[b] = S.iters;
+    }
+}
+
+extern "C" int qp_host_coop_solve(const ldcbf_params* prm, int B, int N, int max_obs, const double* x0,
+                                  const double* theta0, const double* goal, const int8_t* foot, const double* c_eta,
+                                  const int32_t* nobs, const double* delta, double* U, double* X, double* theta,
+                                  double* omega, double* obj, int32_t* status, int32_t* iters) {
+#define COOP_CASE(n, mo) coop_host_batch<n, mo>(prm, B, max_obs, x0, theta0, goal, foot, c_eta, nobs, delta, U, X, theta, omega, obj, status, iters)
+    if (max_obs > 8) return -1;
+    if (max_obs <= 4) {
+        if (N == 1) COOP_CASE(1, 4); else if (N == 2) COOP_CASE(2, 4); else if (N == 3) COOP_CASE(3, 4); else return -1;
+    } else {
+        if (N == 1) COOP_CASE(1, 8); else if (N == 2) COOP_CASE(2, 8); else if (N == 3) COOP_CASE(3, 8); else return -1;
+    }
+#undef COOP_CASE
+    return 0;
+}
+
+// Analysis aid: final active set (row codes, -1 padded) and the order in which rows entered, for one N = 3 scenario.
+extern "C" int qp_host_coop_active_set(const ldcbf_params* prm, int max_obs, const double* x0, double theta0,
+                                       const double* goal, const int8_t* foot, const double* c_eta, int nobs_b,
+                                       double delta, int* codes_out, int* trips_out) {
+    using namespace ldcbf;
+    constexpr int N = 3, MO = 4;
+    if (max_obs > MO) return -1;
+    const StepConst C = make_const(*prm);
+    LaneGroup<1> grp{1u, 0};
+    int ft[N + 1];
+    for (int k = 0; k <= N; ++k) ft[k] = foot[k];
+    double sm[CoopShape<N, MO>::DOUBLES];
+    CoopState<N> s;
+    coop_setup<N, MO, 1>(C, grp, x0[0], x0[1], x0[2], x0[3], theta0, goal[0], goal[1], ft,
+                         reinterpret_cast<const double4*>(c_eta), nobs_b < MO ? nobs_b : MO, delta,
+                         load_limits(C, nullptr, 0), sm, s);
+    while (!s.done) coop_trip<N, MO, 1>(C, grp, sm, s);
+    for (int j = 0; j < 2 * N; ++j) codes_out[j] = j < s.q ? s.code[j] : -1;
+    *trips_out = s.iters;
+    return s.status;
+}
+
+// Analysis aid: per-trip trace (row code being added, active-set size after the trip, most negative slack) of one scenario.
+extern "C" int qp_host_coop_trace(const ldcbf_params* prm, int max_obs, const double* x0, double theta0,
+                                  const double* goal, const int8_t* foot, const double* c_eta, int nobs_b,
+                                  double delta, int* trace /*[3*cap]*/, double* slack /*[cap]*/, int cap) {
+    using namespace ldcbf;
+    constexpr int N = 3, MO = 4;
+    if (max_obs > MO) return -1;
+    const StepConst C = make_const(*prm);
+    LaneGroup<1> grp{1u, 0};
+    int ft[N + 1];
+    for (int k = 0; k <= N; ++k) ft[k] = foot[k];
+    double sm[CoopShape<N, MO>::DOUBLES];
+    CoopState<N> s;
+    coop_setup<N, MO, 1>(C, grp, x0[0], x0[1], x0[2], x0[3], theta0, goal[0], goal[1], ft,
+                         reinterpret_cast<const double4*>(c_eta), nobs_b < MO ? nobs_b : MO, delta,
+                         load_limits(C, nullptr, 0), sm, s);
+    int n = 0;
+    while (!s.done) {
+        const int q0 = s.q;
+        int codes0[2 * N];
+        for (int j = 0; j < 2 * N; ++j) codes0[j] = s.code[j];
+        coop_trip<N, MO, 1>(C, grp, sm, s);
+        if (n < cap && !s.done) {
+            trace[3 * n] = s.p_code; trace[3 * n + 1] = s.q;
+            int dropped = -1;
+            if (s.q < q0) { for (int j = 0; j < q0; ++j) { bool found = false; for (int l = 0; l < s.q; ++l) found |= s.code[l] == codes0[j]; if (!found) dropped = codes0[j]; } }
+            trace[3 * n + 2] = dropped;
+            slack[n] = s.s_p;
+            ++n;
+        }
+    }
+    return n;
 }

@@ -1,0 +1,124 @@
+"""GPU parity of the solver variants behind one ABI: the initial active-set guess (default), the cold start
+(LDCBF_FLAG_COLD_START) and the warp-per-scenario kernel (LDCBF_FLAG_COOP_LANES) must return the same optimum — the
+oracle's — on identical inputs.  Tolerances as in test_gpu_parity.py (BASELINE.json)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mpc
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+TOL_M = 1e-4
+TOL_OBJ = 1e-6
+
+
+@pytest.fixture(scope="module")
+def L():
+    import ldcbf_b200
+    assert torch.cuda.is_available()
+    ldcbf_b200.lib()
+    return ldcbf_b200
+
+
+def cu(a, dt=torch.float64):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dt).cuda()
+
+
+def _step(L, sc, foots, flags, N=3, delta=None):
+    prm = L.default_params(0.4, flags=flags)
+    out = L.mpc_step(prm, cu(sc["state"][:, :4]), cu(sc["state"][:, 4]), cu(sc["goal"]), cu(foots, torch.int8),
+                     cu(sc["verts"]), cu(sc["nverts"], torch.int32), cu(sc["nobs"], torch.int32),
+                     delta=None if delta is None else cu(delta))
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+def _against_oracle(out, sc, foots, N, delta=None):
+    n_ok = 0
+    for b in range(len(sc["state"])):
+        r = mpc.mpc_step(sc["state"][b], sc["goal"][b], sc["rings"][b], [int(v) for v in foots[b]], N=N, sampling_time=0.4,
+                         delta=0.0 if delta is None else float(delta[b]))
+        assert out["status"][b] == r["status"], (b, out["status"][b], r["status"])
+        if r["status"] == 0:
+            n_ok += 1
+            assert np.abs(out["U"][b] - r["U"]).max() <= TOL_M and np.abs(out["X"][b] - r["X"]).max() <= TOL_M, b
+            assert abs(out["obj"][b] - r["obj"]) <= TOL_OBJ * max(1.0, abs(r["obj"])), b
+        else:
+            assert np.all(np.isnan(out["U"][b]))
+    return n_ok
+
+
+@pytest.mark.parametrize("N", (1, 2, 3))
+def test_coop_lanes_match_oracle(L, N):
+    from ldcbf_b200 import scenarios
+    from ldcbf_b200.binding import FLAG_COOP_LANES
+    sc = scenarios.config2(160, seed=40 + N)
+    foots = scenarios.foot_window(sc["right_first"], 0, N)
+    delta = np.where(np.arange(160) % 3 == 0, 0.2, 0.0)
+    out = _step(L, sc, foots, FLAG_COOP_LANES, N=N, delta=delta)
+    assert _against_oracle(out, sc, foots, N, delta) > 120
+
+
+def test_coop_lanes_on_reference_trajectories_and_statuses(L):
+    """The reference's own per-step inputs (both circle runs) through the warp-per-scenario kernel, plus the
+    infeasible (CoM inside the margin) and degenerate (CoM on an edge) statuses."""
+    from ldcbf_b200 import scenarios
+    from ldcbf_b200.binding import FLAG_COOP_LANES
+    rings, states, goals, foots, deltas = helpers.golden_step_inputs()
+    verts, nverts, nobs = scenarios.pack_rings([rings] * len(states))
+    sc = dict(state=states, goal=goals, verts=verts, nverts=nverts, nobs=nobs, rings=[rings] * len(states))
+    out = _step(L, sc, foots, FLAG_COOP_LANES, delta=deltas)
+    assert _against_oracle(out, sc, foots, 3, deltas) == len(states)
+    # delta larger than the clearance: the constant k = 0 row is violated -> status 2, NaN outputs
+    big = np.full(len(states), 5.0)
+    out = _step(L, sc, foots, FLAG_COOP_LANES, delta=big)
+    assert np.all(out["status"] == 2) and np.all(np.isnan(out["obj"]))
+
+
+def test_coop_lanes_eight_obstacles_ragged(L):
+    """The MO = 8 instantiation with ragged obstacle counts (including none)."""
+    from ldcbf_b200 import scenarios
+    from ldcbf_b200.binding import FLAG_COOP_LANES
+    rs = np.random.default_rng(12)
+    base = scenarios.config2(64, seed=77)
+    rings_list = []
+    for b in range(64):
+        n = int(rs.integers(0, 9))
+        rings = []
+        for o in range(n):
+            ctr = rs.uniform((1.5, -3.0), (5.0, 3.0))
+            ang = np.sort(rs.uniform(0, 2 * np.pi, 6))
+            rings.append(ctr + 0.25 * np.column_stack((np.cos(ang), np.sin(ang))))
+        rings_list.append(rings)
+    verts, nverts, nobs = scenarios.pack_rings(rings_list, max_obs=8)
+    sc = dict(state=base["state"], goal=base["goal"], verts=verts, nverts=nverts, nobs=nobs, rings=rings_list)
+    foots = scenarios.foot_window(base["right_first"], 0, 3)
+    out = _step(L, sc, foots, FLAG_COOP_LANES)
+    assert _against_oracle(out, sc, foots, 3) > 30
+
+
+def test_guess_cold_and_coop_agree_at_full_size(L):
+    """Config 2 at its full size (4096): the three variants agree with each other to 1e-6 m (a vertex with multipliers
+    ~3e4 sits in this batch, see test_solver_host_build.py), the guess needs fewer than half the iterations."""
+    from ldcbf_b200 import scenarios
+    from ldcbf_b200.binding import FLAG_COLD_START, FLAG_COOP_LANES
+    sc = scenarios.config2(4096, seed=0)
+    foots = scenarios.foot_window(sc["right_first"], 0, 3)
+    guess = _step(L, sc, foots, 0)
+    cold = _step(L, sc, foots, FLAG_COLD_START)
+    assert np.array_equal(guess["status"], cold["status"])
+    ok = cold["status"] == 0
+    assert ok.sum() > 4000
+    assert np.abs(guess["U"][ok] - cold["U"][ok]).max() <= 1e-6 and np.abs(guess["X"][ok] - cold["X"][ok]).max() <= 1e-6
+    assert np.abs(guess["obj"][ok] - cold["obj"][ok]).max() <= 1e-7 * np.abs(cold["obj"][ok]).max()
+    assert guess["iters"].mean() < 0.5 * cold["iters"].mean()
+    for lo in range(0, 4096, 1024):          # the cooperative kernel takes batches of at most 1024
+        sub = {k: (v[lo:lo + 1024] if k != "rings" else v[lo:lo + 1024]) for k, v in sc.items() if k in
+               ("state", "goal", "verts", "nverts", "nobs", "rings")}
+        coop = _step(L, sub, foots[lo:lo + 1024], FLAG_COOP_LANES | FLAG_COLD_START)
+        assert np.array_equal(coop["status"], cold["status"][lo:lo + 1024])
+        okc = coop["status"] == 0
+        assert np.abs(coop["U"][okc] - cold["U"][lo:lo + 1024][okc]).max() <= 1e-6
+        assert np.array_equal(coop["theta"], cold["theta"][lo:lo + 1024])

@@ -18,7 +18,8 @@ CSRC = os.path.join(ROOT, "humanoid-navigation-using-mpc-ldcbf_b200", "csrc")
 @pytest.fixture(scope="module")
 def host_lib():
     so = os.path.join(HARNESS, "libqp_host.so")
-    srcs = [os.path.join(HARNESS, "qp_host.cu"), os.path.join(CSRC, "mpc_qp.cuh"), os.path.join(CSRC, "ldcbf_common.cuh")]
+    srcs = [os.path.join(HARNESS, "qp_host.cu"), os.path.join(CSRC, "mpc_qp.cuh"), os.path.join(CSRC, "mpc_qp_coop.cuh"),
+            os.path.join(CSRC, "ldcbf_common.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.run(["nvcc", "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"),
                         "-I", CSRC, "-gencode", "arch=compute_100a,code=sm_100a", srcs[0], "-o", so], check=True)
@@ -26,22 +27,28 @@ def host_lib():
     return ctypes.CDLL(so)
 
 
-def host_solve(lib, states, goals, foots, c_eta, nobs, deltas, sampling_time=0.4):
+def host_solve(lib, states, goals, foots, c_eta, nobs, deltas, sampling_time=0.4, coop=False, flags=0):
     import ldcbf_b200
     from ldcbf_b200.binding import LdcbfParams
     B = len(states)
     prm = LdcbfParams()
     ldcbf_b200.lib().ldcbf_params_default(ctypes.byref(prm))
     prm.sampling_time = sampling_time
+    prm.flags = flags
     f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
     x0, th, g = f64(states[:, :4]), f64(states[:, 4]), f64(goals)
     ft, ce, no, dl = np.ascontiguousarray(foots, dtype=np.int8), f64(c_eta), np.ascontiguousarray(nobs, dtype=np.int32), f64(deltas)
     out = dict(U=np.zeros((B, 3, 2)), X=np.zeros((B, 4, 4)), theta=np.zeros((B, 4)), omega=np.zeros((B, 3)),
                obj=np.zeros(B), status=np.zeros(B, np.int32), iters=np.zeros(B, np.int32))
     P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-    rc = lib.qp_host_solve_n3(ctypes.byref(prm), B, ce.shape[1], P(x0), P(th), P(g), P(ft), P(ce), P(no), P(dl),
-                              P(out["U"]), P(out["X"]), P(out["theta"]), P(out["omega"]), P(out["obj"]),
-                              P(out["status"]), P(out["iters"]))
+    if coop:      # the cooperative kernel's solver (csrc/mpc_qp_coop.cuh) with a group of one lane
+        rc = lib.qp_host_coop_solve(ctypes.byref(prm), B, 3, ce.shape[1], P(x0), P(th), P(g), P(ft), P(ce), P(no), P(dl),
+                                    P(out["U"]), P(out["X"]), P(out["theta"]), P(out["omega"]), P(out["obj"]),
+                                    P(out["status"]), P(out["iters"]))
+    else:
+        rc = lib.qp_host_solve_n3(ctypes.byref(prm), B, ce.shape[1], P(x0), P(th), P(g), P(ft), P(ce), P(no), P(dl),
+                                  P(out["U"]), P(out["X"]), P(out["theta"]), P(out["omega"]), P(out["obj"]),
+                                  P(out["status"]), P(out["iters"]))
     assert rc == 0
     return out
 
@@ -66,15 +73,17 @@ def compare(out, ref):
     return worst
 
 
-def test_host_build_on_reference_trajectories(host_lib):
+@pytest.mark.parametrize("coop", [False, True])
+def test_host_build_on_reference_trajectories(host_lib, coop):
     rings, states, goals, foots, deltas = helpers.golden_step_inputs()
     ce, nobs = c_eta_of(states, [rings] * len(states))
-    out = host_solve(host_lib, states, goals, foots, ce, nobs, deltas)
+    out = host_solve(host_lib, states, goals, foots, ce, nobs, deltas, coop=coop)
     ref = helpers.oracle_steps(states, goals, foots, [rings] * len(states), deltas)
     assert compare(out, ref) < 1e-8
 
 
-def test_host_build_on_closed_loops_with_margin(host_lib):
+@pytest.mark.parametrize("coop", [False, True])
+def test_host_build_on_closed_loops_with_margin(host_lib, coop):
     """Closed loops driven by the host build itself (delta = 0.3 and 0, incl. states that end infeasible)."""
     geo = helpers.load_geo()
     rings = helpers.map_rings(geo, "circles")
@@ -84,7 +93,8 @@ def test_host_build_on_closed_loops_with_margin(host_lib):
         for k in range(120):
             st = state[None, :]
             ce, nobs = c_eta_of(st, [rings])
-            out = host_solve(host_lib, st, np.array([[6.0, -3.0]]), np.array([s_v[k:k + 4]]), ce, nobs, np.array([delta]))
+            out = host_solve(host_lib, st, np.array([[6.0, -3.0]]), np.array([s_v[k:k + 4]]), ce, nobs, np.array([delta]),
+                             coop=coop)
             r = mpc.mpc_step(state, (6, -3), rings, s_v[k:k + 4], sampling_time=0.4, delta=delta)
             assert compare(out, [r]) < 1e-8, (delta, k)
             if r["status"] != 0 or r["obj"] < 0.05:
@@ -93,12 +103,13 @@ def test_host_build_on_closed_loops_with_margin(host_lib):
         assert k > 20
 
 
-def test_host_build_on_config2_batch(host_lib):
+@pytest.mark.parametrize("coop", [False, True])
+def test_host_build_on_config2_batch(host_lib, coop):
     from ldcbf_b200 import scenarios
     sc = scenarios.config2(512, seed=0)
     foots = scenarios.foot_window(sc["right_first"], 0, 3)
     ce, nobs = c_eta_of(sc["state"], sc["rings"])
-    out = host_solve(host_lib, sc["state"], sc["goal"], foots, ce, nobs, np.zeros(512))
+    out = host_solve(host_lib, sc["state"], sc["goal"], foots, ce, nobs, np.zeros(512), coop=coop)
     ref = helpers.oracle_steps(sc["state"], sc["goal"], foots, sc["rings"], np.zeros(512))
     # scenario 50 sits on an ill-conditioned vertex (two nearly anti-parallel velocity rows, multipliers ~3e4)
     # where the NNLS oracle itself only reaches a complementarity residual of 5e-5: 1e-6 there, 1e-9 elsewhere
@@ -106,6 +117,22 @@ def test_host_build_on_config2_batch(host_lib):
     d = np.array([np.abs(out["U"][b] - r["U"]).max() for b, r in enumerate(ref) if r["status"] == 0])
     assert np.percentile(d, 99) < 1e-9
     assert out["iters"].max() <= 60
+
+
+def test_host_build_initial_guess_is_exact_and_cheaper(host_lib):
+    """The default start (all velocity rows on the goal's side, repaired by the warm start) against the cold start
+    (LDCBF_FLAG_COLD_START = 2): same optimum, fewer than half the iterations (warm-start rounds counted)."""
+    from ldcbf_b200 import scenarios
+    sc = scenarios.config2(768, seed=5)
+    foots = scenarios.foot_window(sc["right_first"], 0, 3)
+    ce, nobs = c_eta_of(sc["state"], sc["rings"])
+    guess = host_solve(host_lib, sc["state"], sc["goal"], foots, ce, nobs, np.zeros(768))
+    cold = host_solve(host_lib, sc["state"], sc["goal"], foots, ce, nobs, np.zeros(768), flags=2)
+    assert np.array_equal(guess["status"], cold["status"])
+    ok = cold["status"] == 0
+    assert np.abs(guess["U"][ok] - cold["U"][ok]).max() < 1e-6
+    assert np.percentile(np.abs(guess["U"][ok] - cold["U"][ok]).max(axis=(1, 2)), 99) < 1e-9
+    assert guess["iters"].mean() < 0.5 * cold["iters"].mean()
 
 
 def test_host_build_with_streamed_obstacles(host_lib):
