@@ -21,8 +21,23 @@ __device__ __forceinline__ double dot2(double a0, double a1, double b0, double b
     return __fma_rn(a1, b1, __dmul_rn(a0, b0));   // numpy's 2-element dot on the reference build
 }
 
-// Closest point of segment AB to P.  Returns the comparison key of the edge (the distance when EXACT, the
-// squared distance otherwise), writes c; `cross` is incremented when the edge A->B toggles the crossing parity.
+// The reference keeps the first edge whose ROUNDED distance sqrt(d2) is strictly smaller (`dist < min_dist`,
+// ObstaclesUtils.py:91-94).  key_less<true>(a, b) decides RN(sqrt(a)) < RN(sqrt(b)) from the squared distances
+// without taking a square root in all but near-tie cases:  a >= b  =>  sqrt(a) >= sqrt(b)  =>  not smaller (this
+// covers the common exact tie of two edges clamping to their shared vertex);  a < b (1 - 2^-48)  =>  sqrt(a) <
+// sqrt(b) (1 - 2^-49), which two roundings of relative size 2^-53 cannot reverse or close;  in between (a relative
+// gap below 2^-48: practically never) both roots are taken.  Saves one of the two square roots per edge.
+template <bool EXACT>
+__device__ __forceinline__ bool key_less(double a, double b) {
+    if (!EXACT) return a < b;
+    if (!(a < b)) return false;
+    if (a < __fma_rn(-0x1p-48, b, b)) return true;
+    return __dsqrt_rn(a) < __dsqrt_rn(b);
+}
+constexpr double KEY_NONE = 1.0e300;      // "no edge yet": finite so that the threshold above stays finite
+
+// Closest point of segment AB to P.  Returns the squared distance d2 (EXACT: dot2 in the reference's operation
+// order, compared through key_less), writes c; `cross` is incremented when the edge A->B toggles the crossing parity.
 template <bool EXACT>
 __device__ __forceinline__ double edge_closest(double px, double py, double2 A, double2 Bv, double& cx, double& cy,
                                                int& cross) {
@@ -42,7 +57,7 @@ __device__ __forceinline__ double edge_closest(double px, double py, double2 A, 
                               __dmul_rn(__dsub_rn(Bv.x, px), __dsub_rn(A.y, Bv.y));
             cross += (side == f1);
         }
-        return __dsqrt_rn(dot2(dx, dy, dx, dy));
+        return dot2(dx, dy, dx, dy);
     } else {
         const double apx = px - A.x, apy = py - A.y;
         const double abx = Bv.x - A.x, aby = Bv.y - A.y;
@@ -83,14 +98,14 @@ __device__ __forceinline__ double4 finish_halfplane(double px, double py, double
 // Serial walk over a ring of V vertices (global or shared memory): first strict minimum, edge order 0..V-1.
 template <bool EXACT>
 __device__ __forceinline__ double4 halfplane_serial(double px, double py, const double2* ring, int V) {
-    double best = INFINITY, bcx = 0.0, bcy = 0.0;
+    double best = KEY_NONE, bcx = 0.0, bcy = 0.0;
     int cross = 0;
     double2 A = ring[0];
     for (int e = 0; e < V; ++e) {
         const double2 Bv = ring[(e + 1 == V) ? 0 : e + 1];
         double cx, cy;
         const double key = edge_closest<EXACT>(px, py, A, Bv, cx, cy, cross);
-        if (key < best) { best = key; bcx = cx; bcy = cy; }
+        if (key_less<EXACT>(key, best)) { best = key; bcx = cx; bcy = cy; }
         A = Bv;
     }
     return finish_halfplane<EXACT>(px, py, bcx, bcy, cross);
