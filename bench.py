@@ -251,7 +251,8 @@ def run_ours(args):
                 "config": {"workload": WORKLOAD, "batch_per_gpu": B, "horizon": N, "obstacles": 3,
                            "per_rank_data": "own copy of the same seeded batch on every rank (equal work per GPU)",
                            "timing": "CUDA events per step, L2 flushed (256 MB write) between timed steps",
-                           "solver": "dual active set (Goldfarb-Idnani) in CoM-position space, fp64"},
+                           "solver": "dual active set (Goldfarb-Idnani) in CoM-position space, fp64; geometric "
+                                     "active-set guess; two racing pivot orders per scenario at this batch size"},
                 "p50_step_us": 1e3 * statistics.median(ts), "gpu_launches": 2 * args.steps,
                 "iters_mean": float(iters.mean().item()), "status_counts": status}
 
@@ -272,12 +273,15 @@ def run_ours(args):
             peak_fp64 = max(L.probe_fp64() for _ in range(3))
             flops = float((iters * FLOP_PER_ITER + FLOP_SETUP).sum().item())
             ach = flops / (statistics.mean(t_qp) * 1e-3) / 1e12
-            line["roofline"] = {"bound": "fp64", "kernel": "mpc_qp_kernel<3,4,8>", "achieved": ach, "peak": peak_fp64,
+            line["roofline"] = {"bound": "fp64", "kernel": "mpc_qp_race_kernel<3,4,16>", "achieved": ach, "peak": peak_fp64,
                                 "unit": "TFLOP/s", "frac": ach / peak_fp64, "traffic": profile_traffic(B),
                                 "kernel_ms": statistics.mean(t_qp),
                                 "peak_source": "FP64 FMA-chain probe measured in this run (MEASURED_PEAKS.json has no fp64 entry)",
-                                "note": "B=4096 is 128 warps on 148 SMs: latency-bound by construction; large_batch "
-                                        "shows the same kernel with the GPU full"}
+                                "flop_model": f"sum over scenarios of iters*{FLOP_PER_ITER:.0f} + {FLOP_SETUP:.0f} (iters of the "
+                                              "winning path, warm-start rounds counted as iterations; DESIGN.md §6)",
+                                "note": "B=4096 is 512 half-warps on 592 SM sub-partitions: bound by the instruction "
+                                        "latency of the slowest scenario's path (ncu: 3.9 cycles per issued instruction, "
+                                        "1 warp per sub-partition); large_batch shows the solver with the GPU full"}
             # ---- large batch: the regime where the GPU is full
             line["large_batch"] = large_batch(L, sc, foots, prm, flush, peak_fp64, torch)
             # ---- the other rows of the hot path: closed-loop rollout kernel, LiDAR caster, single-scenario latency

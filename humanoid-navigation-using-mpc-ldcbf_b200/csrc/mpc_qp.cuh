@@ -184,6 +184,7 @@ struct QpState {
     double np[2 * N], nn, s_p, u_p;       // row being added: signed normal, |n|^2, slack, multiplier
     int p_code;                           // ... and its row code 2*id + (upper side)
     unsigned amask;                       // occupied slots
+    int pref;                             // pivot preference of the scan: -1 none, 0 leg rows first, 1 velocity rows first
     int status, iters;
     bool need_scan, done;
 };
@@ -252,6 +253,7 @@ LDCBF_HD void qp_setup(const StepConst& C, double p0x, double v0x, double p0y, d
 #pragma unroll
     for (int k = 1; k <= N; ++k) { s.px[k] = gx; s.py[k] = gy; }
     s.amask = 0;
+    s.pref = -1;
     // AN(j, .): signed normal of slot j (zero when free);  GM(i, j): Gram matrix of the slots (identity on free slots)
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
@@ -265,6 +267,21 @@ LDCBF_HD void qp_setup(const StepConst& C, double p0x, double v0x, double p0y, d
     s.need_scan = true;
     s.status = status;
     s.done = status != LDCBF_STATUS_SOLVED;
+}
+
+// (value, index) tournament over sl[LO .. LO+LEN): the minimum ends in sl[LO], its index in ti[LO]
+template <int LO, int LEN, int NR>
+LDCBF_HD void argmin_range(double (&sl)[NR], int (&ti)[NR]) {
+#pragma unroll
+    for (int n = LEN; n > 1; n = (n + 1) / 2) {
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const int a = LO + i, o = LO + n - 1 - i;
+            const bool take = sl[o] < sl[a];
+            sl[a] = take ? sl[o] : sl[a];
+            ti[a] = take ? ti[o] : ti[a];
+        }
+    }
 }
 
 // One trip of the active-set loop: (scan for the most violated row if the previous trip ended with a full step,)
@@ -312,21 +329,25 @@ LDCBF_HD void qp_trip(const StepConst& C, double* ws, QpState<N, MO>& s) {
                     sl[4 * N + k * MO + o] = s.ex[o] * s.px[kk] + s.ey[o] * s.py[kk] - s.hb[o];
             }
         }
-        // tournament argmin: (value, index) pairs, one compare and three selects per node
+        // tournament argmin: (value, index) pairs, one compare and three selects per node — one tournament per row
+        // family (leg [0,2N), velocity [2N,4N), LDCBF [4N,NR)), then the three winners
         int ti[NR];
 #pragma unroll
         for (int i = 0; i < NR; ++i) ti[i] = i;
-#pragma unroll
-        for (int n = NR; n > 1; n = (n + 1) / 2) {
-#pragma unroll
-            for (int i = 0; i < n / 2; ++i) {
-                const bool take = sl[n - 1 - i] < sl[i];
-                sl[i] = take ? sl[n - 1 - i] : sl[i];
-                ti[i] = take ? ti[n - 1 - i] : ti[i];
-            }
-        }
-        double best = sl[0];
-        int bid = ti[0];
+        argmin_range<0, 2 * N>(sl, ti);
+        argmin_range<2 * N, 2 * N>(sl, ti);
+        argmin_range<4 * N, N * MO>(sl, ti);
+        // Pivot preference (the racing kernel runs the same scenario with two different preferences, mpc_step.cu):
+        // pref = 0 takes the most violated LEG row while any leg row is violated, pref = 1 the most violated
+        // VELOCITY row, pref < 0 (default) the most violated row overall.  Any violated row is a valid pivot of the
+        // dual method; the choice only changes the path, not the optimum.
+        const double b_leg = sl[0], b_vel = sl[2 * N], b_cbf = sl[4 * N];
+        const int i_leg = ti[0], i_vel = ti[2 * N], i_cbf = ti[4 * N];
+        double best = b_leg;
+        int bid = i_leg;
+        if (b_vel < best) { best = b_vel; bid = i_vel; }
+        if (b_cbf < best) { best = b_cbf; bid = i_cbf; }
+        const bool force_leg = s.pref == 0 && b_leg < -C.eps_active, force_vel = s.pref == 1 && b_vel < -C.eps_active;
         // obstacles beyond the register-resident MO: one streaming pass over (c, eta) in global memory (L1/L2)
         for (int o = 0; o < s.ns; ++o) {
             const double4 c4 = s.ces[o];
@@ -338,6 +359,8 @@ LDCBF_HD void qp_trip(const StepConst& C, double* ws, QpState<N, MO>& s) {
             }
         }
         if (!(best < -C.eps_active)) { s.done = true; return; }   // primal feasible: optimal
+        if (force_leg) { best = b_leg; bid = i_leg; }
+        if (force_vel) { best = b_vel; bid = i_vel; }
         const double bsg = (bid < 4 * N && ((upper >> bid) & 1u)) ? -1.0 : 1.0;
         row_normal<N, MO>(bid, bsg, C.gtil, s.rc, s.rs, s.ft, s.ex, s.ey, s.ces, s.ns, s.np);
         double nn = 0.0;

