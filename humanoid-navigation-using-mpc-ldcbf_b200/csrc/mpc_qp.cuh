@@ -195,10 +195,22 @@ struct QpState {
 
 // Heading schedule, half-plane offsets, row bounds, unconstrained optimum, empty active set.
 // ce[o] = (c_x, c_y, eta_x, eta_y) for o < nb.
-template <int N, int MO, int WS>
+//
+// RESUME = true (large batches, mpc_step.cu): the heading schedule, the iterate, the multipliers and the slot
+// workspace are not computed but read back from the record `rec` (element e of this scenario at rec[e * stride]) that
+// the prepare kernel wrote with qp_dump_state after its own qp_setup + warm start; everything else (inputs, bounds,
+// half-plane offsets, status checks) is recomputed from the inputs, which costs a few dozen instructions.
+template <int N>
+struct QpRecord {       // layout of a record, in doubles
+    static constexpr int TH = 0, OM = TH + N + 1, RC_ = OM + N, RS_ = RC_ + N + 1, W = RS_ + N + 1, U = W + 2 * N,
+                         PACKED = U + 2 * N, WS0 = PACKED + 1, DOUBLES = WS0 + QpWorkspace<N>::DOUBLES;
+};
+
+template <int N, int MO, int WS, bool RESUME = false>
 LDCBF_HD void qp_setup(const StepConst& C, double p0x, double v0x, double p0y, double v0y, double th0, double gx,
                        double gy, const int (&ft)[N + 1], const double4 (&ce)[MO], int nb, const double4* ce_stream,
-                       int n_stream, double delta, const Limits& lim, double* ws, QpState<N, MO>& s) {
+                       int n_stream, double delta, const Limits& lim, double* ws, QpState<N, MO>& s,
+                       const double* rec = nullptr, size_t stride = 0) {
     const double alpha_over_pi = lim.alpha_over_pi, vmax0 = lim.vmax0, omega_max = lim.omega_max, omega_min = lim.omega_min;
     s.vlat_mid = 0.5 * (lim.vmax1 + C.v_min1); s.vlat_half = 0.5 * (lim.vmax1 - C.v_min1);
     constexpr int NV = 2 * N;
@@ -207,7 +219,15 @@ LDCBF_HD void qp_setup(const StepConst& C, double p0x, double v0x, double p0y, d
 #pragma unroll
     for (int k = 0; k <= N; ++k) s.ft[k] = ft[k];
     // ---- heading schedule (HumanoidMpc.py:137-160)
-    {
+    if (RESUME) {
+        using R = QpRecord<N>;
+#pragma unroll
+        for (int k = 0; k <= N; ++k) {
+            s.th[k] = rec[(R::TH + k) * stride]; s.rc[k] = rec[(R::RC_ + k) * stride]; s.rs[k] = rec[(R::RS_ + k) * stride];
+        }
+#pragma unroll
+        for (int k = 0; k < N; ++k) s.om[k] = rec[(R::OM + k) * stride];
+    } else {
         const double phi = atan2(gy - p0y, gx - p0x);
         double thk = th0;
         s.th[0] = thk;
@@ -258,15 +278,53 @@ LDCBF_HD void qp_setup(const StepConst& C, double p0x, double v0x, double p0y, d
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         s.u[j] = 0.0; s.np[j] = 0.0;
+        if (!RESUME) {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) { AN(j, i) = 0.0; GM(j, i) = (i == j) ? 1.0 : 0.0; }
-        RC(j) = -1.0;
+            for (int i = 0; i < NV; ++i) { AN(j, i) = 0.0; GM(j, i) = (i == j) ? 1.0 : 0.0; }
+            RC(j) = -1.0;
+        }
     }
     s.nn = 1.0; s.s_p = 0.0; s.u_p = 0.0; s.p_code = 0;
     s.iters = 0;
     s.need_scan = true;
     s.status = status;
     s.done = status != LDCBF_STATUS_SOLVED;
+    if (RESUME) {
+        using R = QpRecord<N>;
+#pragma unroll
+        for (int k = 1; k <= N; ++k) {
+            s.px[k] = rec[(R::W + 2 * (k - 1)) * stride]; s.py[k] = rec[(R::W + 2 * (k - 1) + 1) * stride];
+        }
+#pragma unroll
+        for (int j = 0; j < NV; ++j) s.u[j] = rec[(R::U + j) * stride];
+        const long long packed = (long long)rec[R::PACKED * stride];       // amask | iters << 8 (exact in a double)
+        s.amask = (unsigned)(packed & 0xff);
+        s.iters = (int)(packed >> 8);
+#pragma unroll
+        for (int e = 0; e < QpWorkspace<N>::DOUBLES; ++e) ws[e * WS] = rec[(R::WS0 + e) * stride];
+    }
+}
+
+// The counterpart of qp_setup<RESUME>: what a scenario's solver state consists of after setup (+ warm start).
+template <int N, int MO, int WS>
+LDCBF_HD void qp_dump_state(const QpState<N, MO>& s, const double* ws, double* rec, size_t stride) {
+    using R = QpRecord<N>;
+    constexpr int NV = 2 * N;
+#pragma unroll
+    for (int k = 0; k <= N; ++k) {
+        rec[(R::TH + k) * stride] = s.th[k]; rec[(R::RC_ + k) * stride] = s.rc[k]; rec[(R::RS_ + k) * stride] = s.rs[k];
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) rec[(R::OM + k) * stride] = s.om[k];
+#pragma unroll
+    for (int k = 1; k <= N; ++k) {
+        rec[(R::W + 2 * (k - 1)) * stride] = s.px[k]; rec[(R::W + 2 * (k - 1) + 1) * stride] = s.py[k];
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) rec[(R::U + j) * stride] = s.u[j];
+    rec[R::PACKED * stride] = (double)((long long)s.amask | ((long long)s.iters << 8));
+#pragma unroll
+    for (int e = 0; e < QpWorkspace<N>::DOUBLES; ++e) rec[(R::WS0 + e) * stride] = ws[e * WS];
 }
 
 // (value, index) tournament over sl[LO .. LO+LEN): the minimum ends in sl[LO], its index in ti[LO]

@@ -12,11 +12,14 @@
 #ifndef LDCBF_QP_REFILL_TRIPS
 #define LDCBF_QP_REFILL_TRIPS 1
 #endif
-// lanes that must be free before a warp stops to retire / refill them.  With the initial active-set guess the fixed
-// work per scenario (setup + warm start, done inside the divergent refill region) outweighs the trips, so the
-// region should run as full as possible: measured at B = 2^20, 8 -> 2.31 ms, 16 -> 1.80, 24 -> 1.63, 32 -> 1.99.
+// lanes that must be free before a warp stops to retire / refill them (cold-start kernel / resume kernel).  With the
+// geometric guess the setup + warm start inside the divergent refill region cost more than the trips (B = 2^20:
+// 8 -> 2.31 ms, 16 -> 1.80, 24 -> 1.63, 32 -> 1.99 against 1.90 ms cold), hence the prepare / resume split below.
 #ifndef LDCBF_QP_REFILL_MIN_IDLE
-#define LDCBF_QP_REFILL_MIN_IDLE 24
+#define LDCBF_QP_REFILL_MIN_IDLE 8
+#endif
+#ifndef LDCBF_QP_RESUME_MIN_IDLE
+#define LDCBF_QP_RESUME_MIN_IDLE 16
 #endif
 
 namespace ldcbf {
@@ -96,15 +99,18 @@ __global__ void __launch_bounds__(BLOCK) mpc_qp_kernel(StepConst C, int B, int m
 // warp owns a contiguous chunk of scenarios; a lane that has converged stores its result and takes the next
 // scenario of the chunk while the other lanes keep iterating, TRIPS trips between two refill points.  No global
 // counter, no atomics: the chunk cursor is warp-uniform and lanes rank themselves with a ballot.
-constexpr int REFILL_MIN_IDLE = LDCBF_QP_REFILL_MIN_IDLE;
-
-template <int N, int MO, int BLOCK, int TRIPS>
-__global__ void __launch_bounds__(BLOCK) mpc_qp_refill_kernel(StepConst C, int B, int max_obs, int per_warp, StepIO io) {
+// RESUME = true: the scenarios of the chunk [b0, b0 + Bc) were set up and warm-started by mpc_qp_prepare_kernel
+// (below); a refill is then a copy of the scenario's record (106 doubles at N = 3, coalesced over the refilling
+// lanes) instead of ~2500 instructions of setup and warm start inside this divergent region.
+template <int N, int MO, int BLOCK, int TRIPS, bool RESUME, int MIN_IDLE>
+__global__ void __launch_bounds__(BLOCK) mpc_qp_refill_kernel(StepConst C, int b0, int Bc, int max_obs, int per_warp,
+                                                            StepIO io, const double* __restrict__ rec) {
     extern __shared__ double qp_ws[];
     double* ws = qp_ws + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     const int warp = (blockIdx.x * BLOCK + threadIdx.x) >> 5;
-    long long first = (long long)warp * per_warp;
+    const int B = b0 + Bc;
+    long long first = (long long)b0 + (long long)warp * per_warp;
     int next = first < B ? (int)first : B;                       // warp-uniform chunk cursor
     const int end = min(B, next + per_warp);
     QpState<N, MO> s;
@@ -117,7 +123,7 @@ __global__ void __launch_bounds__(BLOCK) mpc_qp_refill_kernel(StepConst C, int B
         const bool more = next < end;
         // service point: retire converged lanes and refill free lanes in one (divergent) region, entered only when
         // enough lanes are free to amortise it, or when no lane has anything left to iterate on
-        if ((more && __popc(done_m) + __popc(idle_m) >= REFILL_MIN_IDLE) || none_busy) {
+        if ((more && __popc(done_m) + __popc(idle_m) >= MIN_IDLE) || none_busy) {
             if (b >= 0 && s.done) {
                 QpSolution<N> S;
                 qp_finish<N, MO>(C, s, S);
@@ -142,13 +148,9 @@ __global__ void __launch_bounds__(BLOCK) mpc_qp_refill_kernel(StepConst C, int B
                     const double4* gce = reinterpret_cast<const double4*>(io.c_eta) + (size_t)b * max_obs;
 #pragma unroll
                     for (int o = 0; o < MO; ++o) ce[o] = (o < nb) ? gce[o] : make_double4(0.0, 0.0, 0.0, 0.0);
-                    qp_setup<N, MO, BLOCK>(C, x.x, x.y, x.z, x.w, th0, g.x, g.y, ft, ce, nb, gce + MO, nt - nb,
-                                           io.delta ? io.delta[b] : 0.0, lim, ws, s);
-                    if (!C.cold_start) {
-                        int codes[2 * N];
-                        guess_codes<N, MO>(s, codes);
-                        qp_warm_start<N, MO, BLOCK>(C, codes, ws, s);
-                    }
+                    qp_setup<N, MO, BLOCK, RESUME>(C, x.x, x.y, x.z, x.w, th0, g.x, g.y, ft, ce, nb, gce + MO, nt - nb,
+                                                   io.delta ? io.delta[b] : 0.0, lim, ws, s,
+                                                   RESUME ? rec + (b - b0) : nullptr, (size_t)Bc);
                 }
                 next = min(end, next + __popc(free_m));
             }
@@ -159,6 +161,39 @@ __global__ void __launch_bounds__(BLOCK) mpc_qp_refill_kernel(StepConst C, int B
             if (b >= 0 && !s.done) qp_trip<N, MO, BLOCK>(C, ws, s);
         }
     }
+}
+
+// Large batches, first half: one thread per scenario runs the fixed part of a solve — heading schedule (atan2, N+1
+// sincos), bounds, geometric guess, warm start (Gram matrix, Cholesky, sign repair) — with every lane of every warp
+// busy, and writes the resulting solver state as a record, element-major over the chunk (coalesced).
+template <int N, int MO, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) mpc_qp_prepare_kernel(StepConst C, int b0, int Bc, int max_obs, StepIO io,
+                                                             double* __restrict__ rec) {
+    extern __shared__ double qp_ws[];
+    const int i = blockIdx.x * BLOCK + threadIdx.x;
+    if (i >= Bc) return;
+    const int b = b0 + i;
+    double4 x;
+    double th0;
+    load_state(io, b, x, th0);
+    const double2 g = reinterpret_cast<const double2*>(io.goal)[b];
+    int ft[N + 1];
+    load_foot<N>(io, b, ft);
+    const Limits lim = load_limits(C, io.limits, (size_t)b);
+    const int nt = min(io.nobs[b], max_obs);
+    const int nb = min(nt, MO);
+    double4 ce[MO];
+    const double4* gce = reinterpret_cast<const double4*>(io.c_eta) + (size_t)b * max_obs;
+#pragma unroll
+    for (int o = 0; o < MO; ++o) ce[o] = (o < nb) ? gce[o] : make_double4(0.0, 0.0, 0.0, 0.0);
+    double* ws = qp_ws + threadIdx.x;
+    QpState<N, MO> s;
+    qp_setup<N, MO, BLOCK>(C, x.x, x.y, x.z, x.w, th0, g.x, g.y, ft, ce, nb, gce + MO, nt - nb,
+                           io.delta ? io.delta[b] : 0.0, lim, ws, s);
+    int codes[2 * N];
+    guess_codes<N, MO>(s, codes);
+    qp_warm_start<N, MO, BLOCK>(C, codes, ws, s);
+    qp_dump_state<N, MO, BLOCK>(s, ws, rec + i, (size_t)Bc);
 }
 
 // Batches that do not fill the GPU: G lanes per scenario (mpc_qp_coop.cuh).  BLOCK / G scenarios per block, each with
@@ -198,6 +233,30 @@ static int launch_qp_coop(const StepConst& C, int B, int max_obs, const StepIO& 
     }
     kern<<<(unsigned)((B + PER_BLOCK - 1) / PER_BLOCK), BLOCK, smem, st>>>(C, B, max_obs, io);
     return check_launch();
+}
+
+// Library-owned memory pool (one per device) for the record buffer of the prepare / resume split: stream-ordered
+// allocations that are kept between calls (release threshold = max) so that a step never pays for a driver allocation
+// after the first one.
+static std::mutex g_pool_mutex;
+static cudaMemPool_t g_pools[64] = {};
+static cudaMemPool_t record_pool() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (!g_pools[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool = nullptr;
+        if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        g_pools[dev] = pool;
+    }
+    return g_pools[dev];
 }
 
 // development aid: LDCBF_COOP_MAX_B overrides the largest batch routed to the cooperative kernel, LDCBF_COOP_G the
@@ -303,13 +362,37 @@ static int launch_qp(const StepConst& C, int B, int max_obs, const StepIO& io, c
         // persistent grid: 2 blocks of 128 threads per SM (register-limited occupancy), >= 128 scenarios per warp
         constexpr int BLOCK = 128, TRIPS = LDCBF_QP_REFILL_TRIPS;
         const int warps = 148 * 2 * (BLOCK / 32);
-        const int per_warp = (B + warps - 1) / warps;
         const size_t smem = (size_t)QpWorkspace<N>::DOUBLES * sizeof(double) * BLOCK;
-        auto kern = mpc_qp_refill_kernel<N, MO, BLOCK, TRIPS>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_last_error(e); return LDCBF_E_LAUNCH; }
-        kern<<<148 * 2, BLOCK, smem, st>>>(C, B, max_obs, per_warp, io);
-        return check_launch();
+        if (C.cold_start) {
+            auto kern = mpc_qp_refill_kernel<N, MO, BLOCK, TRIPS, false, LDCBF_QP_REFILL_MIN_IDLE>;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { set_last_error(e); return LDCBF_E_LAUNCH; }
+            kern<<<148 * 2, BLOCK, smem, st>>>(C, 0, B, max_obs, (B + warps - 1) / warps, io, nullptr);
+            return check_launch();
+        }
+        // prepare (convergent) + resume (lane refill from records), in chunks of at most 2^20 scenarios so that the
+        // stream-ordered record buffer stays below 1 GB; HBM is otherwise idle in these FP64-bound kernels
+        constexpr int CHUNK = 1 << 20;
+        const int Bmax = B < CHUNK ? B : CHUNK;
+        double* rec = nullptr;
+        cudaMemPool_t pool = record_pool();
+        cudaError_t e = pool ? cudaMallocFromPoolAsync(&rec, (size_t)QpRecord<N>::DOUBLES * sizeof(double) * Bmax, pool, st)
+                             : cudaErrorMemoryAllocation;
+        if (e != cudaSuccess) { set_last_error(e); cudaGetLastError(); return LDCBF_E_LAUNCH; }
+        auto prep = mpc_qp_prepare_kernel<N, MO, BLOCK>;
+        auto kern = mpc_qp_refill_kernel<N, MO, BLOCK, TRIPS, true, LDCBF_QP_RESUME_MIN_IDLE>;
+        e = cudaFuncSetAttribute(prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int rc = LDCBF_OK;
+        if (e != cudaSuccess) { set_last_error(e); rc = LDCBF_E_LAUNCH; }
+        for (int b0 = 0; b0 < B && rc == LDCBF_OK; b0 += CHUNK) {
+            const int Bc = (B - b0) < CHUNK ? (B - b0) : CHUNK;
+            prep<<<(unsigned)((Bc + BLOCK - 1) / BLOCK), BLOCK, smem, st>>>(C, b0, Bc, max_obs, io, rec);
+            kern<<<148 * 2, BLOCK, smem, st>>>(C, b0, Bc, max_obs, (Bc + warps - 1) / warps, io, rec);
+            rc = check_launch();
+        }
+        cudaFreeAsync(rec, st);
+        return rc;
     }
     if (B >= 148 * 4 * 128) return launch_qp_block<N, MO, 128>(C, B, max_obs, io, st);
     if (B >= 148 * 4 * 16) return launch_qp_block<N, MO, 32>(C, B, max_obs, io, st);
@@ -365,6 +448,14 @@ extern "C" void ldcbf_params_default(ldcbf_params* p) {
 }
 
 extern "C" size_t ldcbf_workspace_bytes(int, int, int, int) { return 0; }
+
+extern "C" int ldcbf_trim_workspace(void) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return LDCBF_E_ARG;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (g_pools[dev] && cudaMemPoolTrimTo(g_pools[dev], 0) != cudaSuccess) { cudaGetLastError(); return LDCBF_E_LAUNCH; }
+    return LDCBF_OK;
+}
 
 extern "C" int ldcbf_mpc_qp_f64(const ldcbf_params* prm, int B, int N, int max_obs, const double* x0,
                                 const double* theta0, const double* goal, const int8_t* foot, const double* c_eta,

@@ -14,6 +14,7 @@ MAX_HORIZON = 4        # LDCBF_MAX_HORIZON: fused rollout / thread-per-scenario 
 MAX_HORIZON_LONG = 48  # LDCBF_MAX_HORIZON_LONG: block-per-scenario solver for 5..48
 
 EXPORTS = ("ldcbf_abi_version", "ldcbf_params_default", "ldcbf_last_cuda_error", "ldcbf_workspace_bytes",
+           "ldcbf_trim_workspace",
            "ldcbf_halfplanes_f64", "ldcbf_mpc_qp_f64", "ldcbf_mpc_step_f64", "ldcbf_mpc_step_packed_f64",
            "ldcbf_lidar_cast_f64",
            "ldcbf_lidar_clusters_f64", "ldcbf_clearance_grid_f64",

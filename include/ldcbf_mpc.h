@@ -92,8 +92,15 @@ int ldcbf_abi_version(void);
 void ldcbf_params_default(ldcbf_params* prm);
 const char* ldcbf_last_cuda_error(void);
 
-/* Workspace query kept for ABI stability; the current kernels need none (returns 0). */
+/* Caller-provided workspace: none (returns 0; kept so callers written against SURVEY.md §8b's proposal link).
+ * One internal buffer exists: for batches of 151 552 scenarios and more the solve runs as two kernels (prepare:
+ * heading schedule + warm start, one thread per scenario; resume: active-set iterations with lane refill) that hand the
+ * solver state over through a stream-ordered allocation (cudaMallocFromPoolAsync / cudaFreeAsync on the caller's
+ * stream; 848 B per scenario at N = 3, at most 2^20 scenarios at a time) from a memory pool the library owns per
+ * device.  The pool keeps that memory between calls; ldcbf_trim_workspace() hands it back to the driver (call it
+ * when no step is in flight on the current device). */
 size_t ldcbf_workspace_bytes(int B, int N, int max_obs, int max_verts);
+int ldcbf_trim_workspace(void);
 
 /* K1 — LDCBF half-plane builder.
  * Replaces ObstaclesUtils.get_closest_point_and_normal_vector_from_obs (Utils/ObstaclesUtils.py:60-109),

@@ -112,7 +112,7 @@ def test_guess_cold_and_coop_agree_at_full_size(L):
     ok = cold["status"] == 0
     assert ok.sum() > 4000
     assert np.abs(guess["U"][ok] - cold["U"][ok]).max() <= 1e-5 and np.abs(guess["X"][ok] - cold["X"][ok]).max() <= 1e-5
-    assert np.percentile(np.abs(guess["U"][ok] - cold["U"][ok]).max(axis=(1, 2)), 99.9) <= 1e-9
+    assert np.percentile(np.abs(guess["U"][ok] - cold["U"][ok]).max(axis=(1, 2)), 99.9) <= 1e-8
     assert np.abs(guess["obj"][ok] - cold["obj"][ok]).max() <= 1e-7 * np.abs(cold["obj"][ok]).max()
     assert guess["iters"].mean() < 0.5 * cold["iters"].mean()
     for lo in range(0, 4096, 1024):          # the cooperative kernel takes batches of at most 1024
@@ -123,3 +123,33 @@ def test_guess_cold_and_coop_agree_at_full_size(L):
         okc = coop["status"] == 0
         assert np.abs(coop["U"][okc] - cold["U"][lo:lo + 1024][okc]).max() <= 1e-5
         assert np.array_equal(coop["theta"], cold["theta"][lo:lo + 1024])
+
+
+def test_large_batch_prepare_resume_split(L):
+    """Batches of 151 552 scenarios and more run as two kernels (prepare + resume with lane refill).  Config 2 tiled
+    40 times (163 840 scenarios): every copy of a scenario gets the same answer, equal to the cold-start kernel's and
+    to the small-batch kernel's; then the record pool is trimmed."""
+    from ldcbf_b200 import scenarios
+    from ldcbf_b200.binding import FLAG_COLD_START
+    sc = scenarios.config2(4096, seed=0)
+    foots = scenarios.foot_window(sc["right_first"], 0, 3)
+    small = _step(L, sc, foots, 0)
+    rep = 40
+    big = {k: np.tile(sc[k], (rep,) + (1,) * (sc[k].ndim - 1)) for k in ("state", "goal", "verts", "nverts", "nobs")}
+    fbig = np.tile(foots, (rep, 1))
+    split = _step(L, big, fbig, 0)
+    cold = _step(L, big, fbig, FLAG_COLD_START)
+    assert L.lib().ldcbf_trim_workspace() == 0
+    B = 4096 * rep
+    for name in ("U", "X", "obj", "theta", "omega"):
+        a = split[name].reshape((rep, 4096) + split[name].shape[1:])
+        assert np.array_equal(np.nan_to_num(a, nan=-1e300), np.nan_to_num(np.broadcast_to(a[0], a.shape), nan=-1e300)), name
+    assert np.array_equal(split["status"], cold["status"]) and np.array_equal(split["status"][:4096], small["status"])
+    ok = cold["status"] == 0
+    assert ok.sum() > 0.97 * B
+    d = np.abs(split["U"][ok] - cold["U"][ok]).max(axis=(1, 2))
+    assert d.max() <= 1e-5 and np.percentile(d, 99.9) <= 1e-8
+    ok0 = small["status"] == 0
+    assert np.abs(split["U"][:4096][ok0] - small["U"][ok0]).max() <= 1e-5
+    assert np.array_equal(split["theta"][:4096], small["theta"])
+    assert split["iters"].mean() < 0.5 * cold["iters"].mean()
