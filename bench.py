@@ -316,7 +316,7 @@ def profile_traffic(batch):
     """dram bytes per launch of the dominant kernel from the committed ncu capture, if one exists for this batch."""
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "kernel_summary.json")))
-        return prof["mpc_qp_kernel"]["dram_bytes_per_launch"].get(str(batch))
+        return prof["k2k3"]["dram_bytes_per_launch"].get(str(batch))
     except Exception:
         return None
 
@@ -348,7 +348,8 @@ def large_batch(L, sc, foots, prm, flush, peak_fp64, torch, B=1 << 20):
     hbm_src = "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     gbs_k1 = BYTES_K1 * Bl / (statistics.mean(t_hp) * 1e-3) / 1e9
     return {"batch": Bl, "value": Bl / (statistics.mean(ts) * 1e-3), "unit": UNIT, "ms_per_step": statistics.mean(ts),
-            "roofline": {"bound": "fp64", "kernel": "mpc_qp_refill_kernel<3,4,128>", "achieved": ach, "peak": peak_fp64,
+            "roofline": {"bound": "fp64", "kernel": "mpc_qp_prepare_kernel<3,4,128> + mpc_qp_refill_kernel<3,4,128,resume>",
+                         "achieved": ach, "peak": peak_fp64,
                          "unit": "TFLOP/s", "frac": ach / peak_fp64, "kernel_ms": statistics.mean(t_qp),
                          "traffic": profile_traffic(Bl)},
             "roofline_hbm": {"bound": "hbm", "kernel": "halfplane_kernel<exact>", "achieved": gbs_k1, "peak": hbm_peak,

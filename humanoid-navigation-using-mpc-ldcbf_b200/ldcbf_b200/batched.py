@@ -54,18 +54,43 @@ class BatchedHumanoidMPC:
         """state_host: pinned [B,6] fp64 tensor (p_x, v_x, p_y, v_y, theta, first stance foot +-1).
         One upload, the loop-shaped step (`ldcbf_mpc_step_packed_f64`), one download and a stream synchronise.
         Returns the pinned host tensor next[B,10] = (x_next[4], theta_1, u0_x, u0_y, omega_0, objective, status),
-        reused between calls."""
+        reused between calls.
+
+        The four stream operations (H2D copy, K1, K2+K3, D2H copy) are captured once into a CUDA graph, keyed on the
+        address of `state_host`, and replayed on later calls with the same buffer (a loop that updates its state
+        tensor in place): one graph launch per step instead of four enqueues through Python.  A different buffer,
+        a batch large enough for the two-kernel solve (which allocates stream-ordered memory) or a failed capture
+        use the plain enqueue path."""
         B = self.B
         if self._pinned is None:
             self._pinned = torch.empty((B, 10), dtype=torch.float64).pin_memory()
             self._d_state = torch.empty((B, 6), dtype=torch.float64, device=self.device)
             self._packed = None
+            self._graph, self._graph_key, self._graph_ok = None, None, B < 148 * 2 * 128 * 4
+        key = (state_host.data_ptr(), tuple(state_host.shape))
+        if self._graph_ok and self._graph_key != key:
+            self._enqueue_host_step(state_host)               # eager once: allocations, lazy module loading
+            torch.cuda.current_stream().synchronize()
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue_host_step(state_host)
+                self._graph, self._graph_key = g, key
+            except Exception:                                 # capture refused: keep the plain path
+                self._graph, self._graph_key, self._graph_ok = None, None, False
+                torch.cuda.synchronize()
+        if self._graph is not None and self._graph_key == key:
+            self._graph.replay()
+        else:
+            self._enqueue_host_step(state_host)
+        torch.cuda.current_stream().synchronize()
+        return self._pinned
+
+    def _enqueue_host_step(self, state_host):
         self._d_state.copy_(state_host, non_blocking=True)
         o = self._packed = _b.mpc_step_packed(self.prm, self._d_state, self.goal, self.verts, self.nverts, self.nobs,
                                               N=self.N, delta=self.delta, limits=self.limits, out=self._packed)
         self._pinned.copy_(o["next"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return self._pinned
 
     @property
     def h2d_bytes_per_step(self):

@@ -233,8 +233,19 @@ def test_packed_step_and_host_path_equal_the_plain_step(L):
     assert np.array_equal(nxt[ok, 8], a["obj"].cpu().numpy()[ok])
     assert np.array_equal(b["iters"].cpu().numpy(), a["iters"].cpu().numpy())
     eng = L.BatchedHumanoidMPC(sc["goal"], sc["verts"], sc["nverts"], sc["nobs"], N_horizon=3, sampling_time=0.4)
-    h = eng.step_host(torch.as_tensor(state6).pin_memory()).numpy()
+    pinned = torch.as_tensor(state6).pin_memory()
+    h = eng.step_host(pinned).numpy()
     assert np.array_equal(h[ok], nxt[ok]) and np.array_equal(h[:, 9], nxt[:, 9])
+    # second call with the same buffer replays the captured CUDA graph: it must read the buffer's CURRENT content
+    # (a loop that advances its state in place) ...
+    adv = np.where(ok[:, None], np.column_stack((nxt[:, :5], -state6[:, 5])), state6)
+    pinned.copy_(torch.as_tensor(adv))
+    h2 = eng.step_host(pinned).numpy().copy()
+    c = L.mpc_step_packed(prm, cu(adv), cu(sc["goal"]), verts, nverts, nobs)["next"].cpu().numpy()
+    assert np.array_equal(np.nan_to_num(h2, nan=-1e300), np.nan_to_num(c, nan=-1e300))
+    # ... and a different buffer takes the plain path again with the same result
+    h3 = eng.step_host(torch.as_tensor(adv).pin_memory()).numpy()
+    assert np.array_equal(np.nan_to_num(h3, nan=-1e300), np.nan_to_num(c, nan=-1e300))
 
 
 def test_infeasible_and_degenerate_status(L):
