@@ -153,3 +153,20 @@ def test_large_batch_prepare_resume_split(L):
     assert np.abs(split["U"][:4096][ok0] - small["U"][ok0]).max() <= 1e-5
     assert np.array_equal(split["theta"][:4096], small["theta"])
     assert split["iters"].mean() < 0.5 * cold["iters"].mean()
+
+
+def test_batch_size_invariance_and_empty_batch(L):
+    """A scenario's answer does not depend on what else is in the batch (prefixes of one batch give bit-identical
+    rows, including odd sizes that leave half-filled warps and blocks), and an empty batch is a no-op."""
+    from ldcbf_b200 import scenarios
+    sc = scenarios.config2(33, seed=8)
+    foots = scenarios.foot_window(sc["right_first"], 0, 3)
+    full = _step(L, sc, foots, 0)
+    for B in (1, 2, 3, 17):
+        sub = {k: v[:B] for k, v in sc.items() if k in ("state", "goal", "verts", "nverts", "nobs")}
+        out = _step(L, sub, foots[:B], 0)
+        for name in ("U", "X", "obj", "theta", "omega", "c_eta", "status", "iters"):
+            assert np.array_equal(np.nan_to_num(out[name], nan=-1e300), np.nan_to_num(full[name][:B], nan=-1e300)), (B, name)
+    empty = {k: v[:0] for k, v in sc.items() if k in ("state", "goal", "verts", "nverts", "nobs")}
+    out = _step(L, empty, foots[:0], 0)
+    assert out["U"].shape == (0, 3, 2) and out["status"].shape == (0,)
