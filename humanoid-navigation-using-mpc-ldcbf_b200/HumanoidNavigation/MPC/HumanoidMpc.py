@@ -29,6 +29,15 @@ conf["OMEGA_MIN"] = -conf["OMEGA_MAX"]
 
 ASSETS_PATH = os.path.dirname(config_dir) + "/Assets/Animations/res.gif"
 
+# The reference hands the QP to an interior-point solver (IPOPT, tol 1e-5, :98-100): its iterates stay strictly inside
+# every LDCBF half-plane, so the CoM never comes to lie exactly ON an obstacle edge.  The exact solver used here puts
+# it there whenever an LDCBF row is active, and the next step's normal (x - c)/||x - c|| [ObstaclesUtils.py:98-107]
+# is then decided by rounding (inside / outside): the closed loop of the basic simulation ends "infeasible" around
+# step 28 instead of at the goal.  The mirror therefore keeps the clearance an interior-point iterate has, 1e-6 m:
+# within BASELINE.json's tolerances (LDCBF rows to 1e-6, trajectories to 1e-4 m), and the basic simulation reaches the
+# goal in 85 steps (reference: 86).  Set to 0.0 for the bare QP; the C ABI and the batched front-end take delta as given.
+INTERIOR_MARGIN = 1e-6
+
 
 class HumanoidMPC:
     """MPC of "Real-Time Safe Bipedal Robot Navigation using Linear Discrete Control Barrier Functions" (Peng et al.)."""
@@ -74,6 +83,10 @@ class HumanoidMPC:
         c, eta = ObstaclesUtils.closest_points_and_normals(np.array([x_k, y_k]), self.obstacles)
         return [ci.reshape(2, 1) for ci in c], [ei.reshape(2, 1) for ei in eta]
 
+    def _delta(self):
+        """LDCBF margin handed to the kernels: the variant's `distance_from_obstacles` plus INTERIOR_MARGIN."""
+        return float(self.distance_from_obstacles) + float(INTERIOR_MARGIN)
+
     def _params(self):
         # conf is read at call time: bounds_tuning.py:22-26 mutates it between runs
         return ldcbf_b200.params_from_conf(conf, self.sampling_time)
@@ -88,7 +101,7 @@ class HumanoidMPC:
             ce[0, o, 2:] = np.asarray(list_eta[o]).ravel()
         out = ldcbf_b200.mpc_qp(self._params(), t(state[None, :4]), t(state[None, 4]), t(np.asarray(self.goal)[None, :]),
                                 t(np.asarray(foot)[None, :], torch.int8), t(ce), t([n], torch.int32),
-                                delta=t([float(self.distance_from_obstacles)]))
+                                delta=t([self._delta()]))
         return {k: v.cpu().numpy()[0] for k, v in out.items()}
 
     def _hooks_overridden(self):
@@ -116,7 +129,7 @@ class HumanoidMPC:
                                t([1 if self.start_with_right_foot else 0], torch.int8), t(verts),
                                t(nverts, torch.int32), t(nobs, torch.int32), T=self.num_inputs, N=self.N_horizon,
                                max_steps_per_goal=self.num_inputs,
-                               delta=t([float(self.distance_from_obstacles)]))
+                               delta=t([self._delta()]))
         K = int(r["steps"].item())
         self.last_status = int(r["status"].item())
         X = r["traj_X"][0].cpu().numpy().T            # [5, T+1]

@@ -481,18 +481,33 @@ LDCBF_HD void qp_trip(const StepConst& C, double* ws, QpState<N, MO>& s) {
     }
     const bool dependent = !(zz > 1e-13 * s.nn) || s.amask == (1u << NV) - 1u;
     // dual step length t1 = min u_j / r_j over r_j > 0, compared by cross-multiplication
-    double t1n = 1.0, t1d = 0.0;          // t1 = t1n / t1d, "infinite" while t1d == 0
-    int ldrop = -1;
+    // as a tournament over (numerator, denominator, slot) triples — depth log2(NV) instead of a chain of NV
+    // dependent compare-and-selects; (1, 0) stands for "no candidate" and loses against every real one
+    double tn[NV], td[NV];
+    int tj[NV];
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-        if (((s.amask >> j) & 1u) && r[j] > 1e-13) {
-            if (ldrop < 0 || s.u[j] * t1d < t1n * r[j]) { t1n = s.u[j]; t1d = r[j]; ldrop = j; }
+        const bool cand = ((s.amask >> j) & 1u) && r[j] > 1e-13;
+        tn[j] = cand ? s.u[j] : 1.0; td[j] = cand ? r[j] : 0.0; tj[j] = cand ? j : -1;
+    }
+#pragma unroll
+    for (int n = NV; n > 1; n = (n + 1) / 2) {
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const int o = n - 1 - i;
+            const bool take = tn[o] * td[i] < tn[i] * td[o];
+            tn[i] = take ? tn[o] : tn[i]; td[i] = take ? td[o] : td[i]; tj[i] = take ? tj[o] : tj[i];
         }
     }
+    const double t1n = tn[0], t1d = td[0];          // t1 = t1n / t1d, "infinite" while t1d == 0
+    const int ldrop = tj[0];
     // full step t2 = -s_p / zz
     const bool full = !dependent && (ldrop < 0 || (-s.s_p) * t1d <= t1n * zz);
     if (!full && ldrop < 0) { s.status = LDCBF_STATUS_INFEASIBLE; s.done = true; return; }
-    const double t = full ? (-s.s_p) / zz : t1n / t1d;
+    // one division, not two (a 123-cycle chain on B200).  A reciprocal seed + two Newton steps (60 cycles, 1-2 ulp)
+    // was tried: 2 % faster, but a full step then no longer lands its row on the bound to the last bit, and the
+    // closed loop of config 1 with delta = 0 ended on an obstacle edge (status 3) at step 31 instead of at the goal.
+    const double t = (full ? -s.s_p : t1n) / (full ? zz : t1d);
 #pragma unroll
     for (int j = 0; j < NV; ++j) s.u[j] -= t * r[j];
     s.u_p += t;
@@ -626,14 +641,14 @@ LDCBF_HD void qp_warm_start(const StepConst& C, const int (&codes)[2 * N], doubl
                 GM(j, l) = g2; GM(l, j) = g2;
             }
         }
-        double mind = INFINITY;
+        bool indep = true;      // every pivot above 1e-10 of its diagonal entry (compared without the division)
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             double dj = GM(j, j);
             const double diag = dj;
 #pragma unroll
             for (int l = 0; l < j; ++l) dj -= L[j][l] * L[j][l];
-            mind = fmin(mind, dj / diag);
+            indep = indep && dj > 1e-10 * diag;
             const double inv = rsqrt_f64(fmax(dj, 1e-300));
             L[j][j] = inv;
 #pragma unroll
@@ -644,7 +659,7 @@ LDCBF_HD void qp_warm_start(const StepConst& C, const int (&codes)[2 * N], doubl
                 L[i][j] = v * inv;
             }
         }
-        if (!(mind > 1e-10)) { fail = true; break; }          // dependent guess
+        if (!indep) { fail = true; break; }                     // dependent guess
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             double v = ((mask >> j) & 1u) ? rhs[j] : 0.0;
