@@ -111,4 +111,30 @@ __device__ __forceinline__ double4 halfplane_serial(double px, double py, const 
     return finish_halfplane<EXACT>(px, py, bcx, bcy, cross);
 }
 
+// G lanes share a ring: lane l takes edges l, l + G, ..., an xor butterfly merges the partial results by the rule of
+// halfplane_split_kernel (order by the rounded distance, ties towards the lower edge index = the first strict minimum
+// of the serial walk; crossing counts are summed).  Every lane returns the same (c, eta), bit-equal to the serial walk.
+template <bool EXACT, int G>
+__device__ __forceinline__ double4 halfplane_group(double px, double py, const double2* ring, int V, int lane,
+                                                   unsigned gmask) {
+    if (G == 1) return halfplane_serial<EXACT>(px, py, ring, V);
+    double best = KEY_NONE, bcx = 0.0, bcy = 0.0;
+    int be = 0x7fffffff, cross = 0;
+    for (int e = lane; e < V; e += G) {
+        const double2 A = __ldg(ring + e), Bv = __ldg(ring + ((e + 1 == V) ? 0 : e + 1));
+        double cx, cy;
+        const double key = edge_closest<EXACT>(px, py, A, Bv, cx, cy, cross);
+        if (key_less<EXACT>(key, best)) { best = key; bcx = cx; bcy = cy; be = e; }
+    }
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) {
+        const double ok = __shfl_xor_sync(gmask, best, off, G);
+        const double ocx = __shfl_xor_sync(gmask, bcx, off, G), ocy = __shfl_xor_sync(gmask, bcy, off, G);
+        const int oe = __shfl_xor_sync(gmask, be, off, G);
+        cross += __shfl_xor_sync(gmask, cross, off, G);
+        if (key_less<EXACT>(ok, best) || (!key_less<EXACT>(best, ok) && oe < be)) { best = ok; bcx = ocx; bcy = ocy; be = oe; }
+    }
+    return finish_halfplane<EXACT>(px, py, bcx, bcy, cross);
+}
+
 }  // namespace ldcbf

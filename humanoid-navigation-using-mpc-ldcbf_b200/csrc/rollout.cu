@@ -24,20 +24,28 @@ struct RolloutIO {
     bool warm_start;
 };
 
-template <int N, int MO, bool EXACT, int BLOCK>
+// G lanes per scenario (small batches): the kernel time is the slowest scenario's chain of sequential steps, and a
+// third of a step is the serial walk over the scenario's rings (52 edges, each a division and a square root).  The G
+// lanes split every ring (halfplane_group, bit-equal to the serial walk) and then all run the same solve in lockstep
+// (same data, same control flow: no divergence, no communication); lane 0 of the group writes.  G = 1 for batches
+// that fill the GPU.
+template <int N, int MO, bool EXACT, int BLOCK, int G>
 __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int T, int n_goals, int max_steps_per_goal,
                                                       int substeps, int max_obs, int max_verts, RolloutIO io) {
     extern __shared__ double qp_ws[];
-    const int b = blockIdx.x * BLOCK + threadIdx.x;
-    if (b >= B) return;
+    const int b = (blockIdx.x * BLOCK + threadIdx.x) / G;
+    if (b >= B) return;                                       // whole groups leave together (G divides BLOCK)
+    const int glane = threadIdx.x % G;
+    const bool writer = glane == 0;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << ((threadIdx.x & 31) / G * G));
     double px = io.state[5 * (size_t)b], vx = io.state[5 * (size_t)b + 1], py = io.state[5 * (size_t)b + 2],
            vy = io.state[5 * (size_t)b + 3], th = io.state[5 * (size_t)b + 4];
     const bool right_first = io.right_first[b] != 0;
     const int nb = min(io.nobs[b], MO);
     const double dl = io.delta ? io.delta[b] : 0.0;
     const Limits lim = load_limits(C, io.limits, (size_t)b);
-    double* tX = io.traj_X ? io.traj_X + (size_t)b * (T + 1) * 5 : nullptr;
-    double* tU = io.traj_U ? io.traj_U + (size_t)b * T * 3 : nullptr;
+    double* tX = (io.traj_X && writer) ? io.traj_X + (size_t)b * (T + 1) * 5 : nullptr;
+    double* tU = (io.traj_U && writer) ? io.traj_U + (size_t)b * T * 3 : nullptr;
     if (tX) { tX[0] = px; tX[1] = vx; tX[2] = py; tX[3] = vy; tX[4] = th; }
 
     int gi = 0, kstep = 0, total = 0, solves = 0, last_status = LDCBF_STATUS_SOLVED;
@@ -45,11 +53,11 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
 #pragma unroll
     for (int j = 0; j < 2 * N; ++j) warm[j] = -1;
     double last_obj = INFINITY, ux = 0.0, uy = 0.0;
-    for (int i = 0; i < n_goals; ++i) io.goal_steps[(size_t)b * n_goals + i] = 0;
+    if (writer) for (int i = 0; i < n_goals; ++i) io.goal_steps[(size_t)b * n_goals + i] = 0;
 
     while (gi < n_goals && total < T) {
         if (last_obj < C.stop_objective || kstep >= max_steps_per_goal) {     // :392 / loop exhausted
-            io.goal_steps[(size_t)b * n_goals + gi] = kstep;
+            if (writer) io.goal_steps[(size_t)b * n_goals + gi] = kstep;
             ++gi; kstep = 0; last_obj = INFINITY;
 #pragma unroll
             for (int j = 0; j < 2 * N; ++j) warm[j] = -1;                      // a fresh run per sub-goal
@@ -65,7 +73,9 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
                 ce[o] = make_double4(0.0, 0.0, 0.0, 0.0);
                 if (o < nb) {
                     const int V = min(io.nverts[(size_t)b * max_obs + o], max_verts);
-                    if (V > 0) ce[o] = halfplane_serial<EXACT>(px, py, io.verts + ((size_t)b * max_obs + o) * max_verts, V);
+                    if (V > 0)
+                        ce[o] = halfplane_group<EXACT, G>(px, py, io.verts + ((size_t)b * max_obs + o) * max_verts, V,
+                                                          glane, gmask);
                 }
             }
             int ft[N + 1];
@@ -88,10 +98,10 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
                 qp_finish<N, MO>(C, qs, S);
                 shift_codes<N, MO, BLOCK>(qs, ws, warm);
             }
-            ++solves;
+            solves += writer ? 1 : 0;
             last_status = S.status;
             if (S.status != LDCBF_STATUS_SOLVED) {                                    // :419-429 break
-                io.goal_steps[(size_t)b * n_goals + gi] = kstep;
+                if (writer) io.goal_steps[(size_t)b * n_goals + gi] = kstep;
                 ++gi; kstep = 0; last_obj = INFINITY;
 #pragma unroll
                 for (int j = 0; j < 2 * N; ++j) warm[j] = -1;
@@ -117,11 +127,13 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
         ++total; ++kstep;
         if (tX) { double* x = tX + 5 * total; x[0] = px; x[1] = vx; x[2] = py; x[3] = vy; x[4] = th; }
     }
-    if (gi < n_goals) io.goal_steps[(size_t)b * n_goals + gi] = kstep;
-    io.state[5 * (size_t)b] = px; io.state[5 * (size_t)b + 1] = vx; io.state[5 * (size_t)b + 2] = py;
-    io.state[5 * (size_t)b + 3] = vy; io.state[5 * (size_t)b + 4] = th;
-    io.steps[b] = total;
-    io.status[b] = last_status;
+    if (writer) {
+        if (gi < n_goals) io.goal_steps[(size_t)b * n_goals + gi] = kstep;
+        io.state[5 * (size_t)b] = px; io.state[5 * (size_t)b + 1] = vx; io.state[5 * (size_t)b + 2] = py;
+        io.state[5 * (size_t)b + 3] = vy; io.state[5 * (size_t)b + 4] = th;
+        io.steps[b] = total;
+        io.status[b] = last_status;
+    }
     if (io.total_solves) {
         // one atomic per warp, whatever subset of its lanes is still here (blocks of 8 threads, ragged last block)
         const unsigned m = __activemask();
@@ -130,16 +142,16 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
     }
 }
 
-template <int N, int MO, bool EXACT, int BLOCK>
+template <int N, int MO, bool EXACT, int BLOCK, int G = 1>
 static int launch_rollout_block(const StepConst& C, int B, int T, int n_goals, int msg, int sub, int max_obs,
                                 int max_verts, const RolloutIO& io, cudaStream_t st) {
     const size_t smem = (size_t)QpWorkspace<N>::DOUBLES * sizeof(double) * BLOCK;
-    auto kern = rollout_kernel<N, MO, EXACT, BLOCK>;
+    auto kern = rollout_kernel<N, MO, EXACT, BLOCK, G>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_last_error(e); return LDCBF_E_LAUNCH; }
     }
-    kern<<<(unsigned)((B + BLOCK - 1) / BLOCK), BLOCK, smem, st>>>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io);
+    kern<<<(unsigned)(((size_t)B * G + BLOCK - 1) / BLOCK), BLOCK, smem, st>>>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io);
     return check_launch();
 }
 
@@ -148,6 +160,13 @@ static int launch_rollout(const StepConst& C, int B, int T, int n_goals, int msg
                           const RolloutIO& io, cudaStream_t st) {
     // 32-lane warps also for small batches: 8-lane blocks (as in the step kernels) were measured — no change at
     // B = 4096 (5.4 ms: the kernel time is the slowest scenario's 150 sequential steps), 18 -> 22 ms at B = 8192
+    // the GPU has idle lanes: 4 per scenario, 8 scenarios per warp.  Measured at B = 4096 (config 2, warm / cold):
+    // 1 lane 5.42 / 6.28 ms, 4 lanes 5.01 / 5.45 ms, 8 lanes 7.35 / 6.00 ms (eight times the warps of this large kernel
+    // at different places in its code: the time then goes to instruction fetch).
+    if (B < 148 * 4 * 16 && max_verts > 8) {
+        return io.fast_geometry ? launch_rollout_block<N, MO, false, 32, 4>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st)
+                                : launch_rollout_block<N, MO, true, 32, 4>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
+    }
     const bool big = B >= 148 * 4 * 128;
     if (io.fast_geometry)
         return big ? launch_rollout_block<N, MO, false, 128>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st)
