@@ -284,6 +284,9 @@ def run_ours(args):
                                         "1 warp per sub-partition); large_batch shows the solver with the GPU full"}
             # ---- large batch: the regime where the GPU is full
             line["large_batch"] = large_batch(L, sc, foots, prm, flush, peak_fp64, torch)
+            # the memory-bound kernel of the path against the measured HBM peak (it needs a full GPU to mean anything)
+            line["roofline_hbm"] = dict(line["large_batch"]["roofline_hbm"], batch=line["large_batch"]["batch"],
+                                        algorithmic_bytes_per_scenario=BYTES_K1)
             # ---- the other rows of the hot path: closed-loop rollout kernel, LiDAR caster, single-scenario latency
             line["rollout"] = rollout_bench(L, sc, torch)
             line["rollout_margin_1e-6"] = rollout_bench(L, sc, torch, delta=1e-6)
