@@ -472,7 +472,8 @@ def unknown_env_bench(L, flush, torch, B=16384):
 
 def latency_b1(L, torch, n=200):
     """p50 latency of one MPC step for ONE scenario (config 1: the reference's basic simulation), device-resident
-    inputs, one call of ldcbf_mpc_step_f64 + a stream synchronise."""
+    inputs: (a) one call of ldcbf_mpc_step_f64 through the binding, (b) the same two launches replayed as a CUDA graph
+    (BatchedHumanoidMPC.step(graph=True)); CUDA events around the call, and wall clock including the synchronise."""
     from ldcbf_b200 import scenarios
     rings = scenarios.circle_rings()
     verts, nverts, nobs = scenarios.pack_rings([rings])
@@ -480,20 +481,30 @@ def latency_b1(L, torch, n=200):
     x0, th, g = cu([[0.0, 0, 3, 0]]), cu([0.0]), cu([[6.0, -3.0]])
     ft, v, nv, no = cu([[1, -1, 1, -1]], torch.int8), cu(verts), cu(nverts, torch.int32), cu(nobs, torch.int32)
     prm = L.default_params(0.4)
+    eng = L.BatchedHumanoidMPC(g, v, nv, no, N_horizon=N_HORIZON, sampling_time=0.4)
     out = {}
-    ts, tw = [], []
-    for i in range(n + 20):
-        t0 = time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        L.mpc_step(prm, x0, th, g, ft, v, nv, no, out=out)
-        e1.record()
-        e1.synchronize()
-        if i >= 20:
-            ts.append(e0.elapsed_time(e1) * 1e3)
-            tw.append((time.perf_counter() - t0) * 1e6)
-    return {"p50_device_us": statistics.median(ts), "p50_wall_us": statistics.median(tw),
-            "note": "B=1, config 1 step 0; reference: CasADi/IPOPT per step, not measurable offline"}
+
+    def timed(fn):
+        ts, tw = [], []
+        for i in range(n + 20):
+            t0 = time.perf_counter()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            if i >= 20:
+                ts.append(e0.elapsed_time(e1) * 1e3)
+                tw.append((time.perf_counter() - t0) * 1e6)
+        return statistics.median(ts), statistics.median(tw)
+
+    d0, w0 = timed(lambda: L.mpc_step(prm, x0, th, g, ft, v, nv, no, out=out))
+    d1, w1 = timed(lambda: eng.step(x0, th, ft, graph=True))
+    same = bool(torch.equal(out["U"], eng._out["U"]))
+    return {"p50_device_us": d1, "p50_wall_us": w1, "plain_call_p50_device_us": d0, "plain_call_p50_wall_us": w0,
+            "graph_equals_plain": same,
+            "note": "B=1, config 1 step 0; headline numbers are the CUDA-graph replay of the two launches; reference: "
+                    "CasADi/IPOPT per step, not measurable offline"}
 
 
 def long_horizon_bench(L, torch):

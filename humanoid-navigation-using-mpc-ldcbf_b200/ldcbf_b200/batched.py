@@ -35,6 +35,7 @@ class BatchedHumanoidMPC:
         self.B = self.goal.shape[0]
         self._out = None
         self._pinned = None
+        self._step_graph, self._step_graph_key, self._step_graph_ok = None, None, None
 
     def _dev(self, a, dtype):
         if isinstance(a, torch.Tensor):
@@ -42,11 +43,34 @@ class BatchedHumanoidMPC:
         return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(self.device)
 
     # ---- device-resident step ---------------------------------------------------------------------------
-    def step(self, x0, theta0, foot, goal=None):
+    def step(self, x0, theta0, foot, goal=None, graph=False):
         """One MPC step for all scenarios.  x0[B,4], theta0[B], foot[B,N+1] int8 CUDA tensors.
-        Returns dict(U, X, theta, omega, c_eta, obj, status, iters) of CUDA tensors (reused between calls)."""
-        self._out = _b.mpc_step(self.prm, x0, theta0, self.goal if goal is None else goal, foot, self.verts,
-                                self.nverts, self.nobs, delta=self.delta, limits=self.limits, out=self._out)
+        Returns dict(U, X, theta, omega, c_eta, obj, status, iters) of CUDA tensors (reused between calls).
+
+        graph=True: the two launches (K1, K2+K3) are captured once into a CUDA graph, keyed on the addresses of the
+        input tensors, and replayed while the caller keeps updating those tensors in place — for small batches the
+        time of a step is otherwise mostly the Python-side marshalling of the 24 arguments between the launches."""
+        g = self.goal if goal is None else goal
+        if not graph or self.B >= 148 * 2 * 128 * 4 or self._step_graph_ok is False:
+            self._out = _b.mpc_step(self.prm, x0, theta0, g, foot, self.verts, self.nverts, self.nobs,
+                                    delta=self.delta, limits=self.limits, out=self._out)
+            return self._out
+        key = (x0.data_ptr(), theta0.data_ptr(), foot.data_ptr(), g.data_ptr(), tuple(x0.shape))
+        if self._step_graph_key != key:
+            self._out = _b.mpc_step(self.prm, x0, theta0, g, foot, self.verts, self.nverts, self.nobs,
+                                    delta=self.delta, limits=self.limits, out=self._out)      # eager once: allocations
+            torch.cuda.current_stream().synchronize()
+            try:
+                cg = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(cg):
+                    _b.mpc_step(self.prm, x0, theta0, g, foot, self.verts, self.nverts, self.nobs, delta=self.delta,
+                                limits=self.limits, out=self._out)
+                self._step_graph, self._step_graph_key = cg, key
+            except Exception:
+                self._step_graph, self._step_graph_key, self._step_graph_ok = None, None, False
+                torch.cuda.synchronize()
+                return self.step(x0, theta0, foot, goal)
+        self._step_graph.replay()
         return self._out
 
     # ---- end-to-end step: host buffers in, host buffers out -----------------------------------------------

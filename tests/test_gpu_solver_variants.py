@@ -170,3 +170,24 @@ def test_batch_size_invariance_and_empty_batch(L):
     empty = {k: v[:0] for k, v in sc.items() if k in ("state", "goal", "verts", "nverts", "nobs")}
     out = _step(L, empty, foots[:0], 0)
     assert out["U"].shape == (0, 3, 2) and out["status"].shape == (0,)
+
+
+def test_device_step_graph_replay_reads_current_inputs(L):
+    """BatchedHumanoidMPC.step(graph=True) replays the captured launches on the tensors' CURRENT contents."""
+    from ldcbf_b200 import scenarios
+    sc = scenarios.config2(64, seed=4)
+    foots = scenarios.foot_window(sc["right_first"], 0, 3)
+    eng = L.BatchedHumanoidMPC(sc["goal"], sc["verts"], sc["nverts"], sc["nobs"], N_horizon=3, sampling_time=0.4)
+    x0, th, ft = cu(sc["state"][:, :4]), cu(sc["state"][:, 4]), cu(foots, torch.int8)
+    a = {k: v.clone() for k, v in eng.step(x0, th, ft, graph=True).items()}
+    ref = _step(L, sc, foots, 0)
+    assert np.array_equal(np.nan_to_num(a["U"].cpu().numpy(), nan=-1e300), np.nan_to_num(ref["U"], nan=-1e300))
+    ok = ref["status"] == 0
+    x0[torch.as_tensor(ok).cuda()] = cu(ref["X"][ok][:, 1])          # advance the state tensors in place
+    th[torch.as_tensor(ok).cuda()] = cu(ref["theta"][ok][:, 1])
+    ft.copy_(-ft)
+    b = eng.step(x0, th, ft, graph=True)
+    sc2 = dict(sc, state=np.column_stack((x0.cpu().numpy(), th.cpu().numpy())))
+    ref2 = _step(L, sc2, -foots, 0)
+    for name in ("U", "X", "obj", "status"):
+        assert np.array_equal(np.nan_to_num(b[name].cpu().numpy(), nan=-1e300), np.nan_to_num(ref2[name], nan=-1e300)), name
