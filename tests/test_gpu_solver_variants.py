@@ -191,3 +191,45 @@ def test_device_step_graph_replay_reads_current_inputs(L):
     ref2 = _step(L, sc2, -foots, 0)
     for name in ("U", "X", "obj", "status"):
         assert np.array_equal(np.nan_to_num(b[name].cpu().numpy(), nan=-1e300), np.nan_to_num(ref2[name], nan=-1e300)), name
+
+
+def test_large_batch_split_other_shapes(L):
+    """The prepare / resume pair against the cold-start refill kernel on a shape the other large-batch test does not
+    touch: N = 2, eight obstacle slots with ragged counts, per-scenario margins and limit overrides, and a batch that
+    is not a multiple of anything (151 552 + 37)."""
+    from ldcbf_b200 import scenarios
+    from ldcbf_b200.binding import FLAG_COLD_START
+    rs = np.random.default_rng(21)
+    base = scenarios.config2(2048, seed=31)
+    B = 148 * 2 * 128 * 4 + 37
+    idx = rs.integers(0, 2048, B)
+    state = base["state"][idx] + np.column_stack((rs.uniform(-0.05, 0.05, (B, 1)), np.zeros((B, 3)), rs.uniform(-0.3, 0.3, (B, 1))))
+    goal = base["goal"][idx] + rs.uniform(-0.2, 0.2, (B, 2))
+    verts = np.zeros((B, 8, base["verts"].shape[2], 2))
+    nverts = np.zeros((B, 8), np.int32)
+    verts[:, :3], nverts[:, :3] = base["verts"][idx], base["nverts"][idx]
+    # obstacles 3..7: copies of the first three shifted far away (never active, but they go through every code path)
+    for o in range(3, 8):
+        verts[:, o], nverts[:, o] = base["verts"][idx, o % 3] + np.array([30.0 + o, 25.0]), base["nverts"][idx, o % 3]
+    nobs = rs.integers(0, 9, B).astype(np.int32)
+    delta = np.where(rs.random(B) < 0.5, 0.0, rs.uniform(0.0, 0.2, B))
+    limits = np.full((B, 6), np.nan)
+    sel = rs.random(B) < 0.3
+    limits[sel, 0], limits[sel, 1] = rs.uniform(2.0, 4.0, sel.sum()), rs.uniform(0.4, 0.9, sel.sum())
+    foots = scenarios.foot_window(base["right_first"][idx], 0, 2)
+    args = (cu(state[:, :4]), cu(state[:, 4]), cu(goal), cu(foots, torch.int8), cu(verts), cu(nverts, torch.int32),
+            cu(nobs, torch.int32))
+    outs = []
+    for flags in (0, FLAG_COLD_START):
+        o = L.mpc_step(L.default_params(0.4, flags=flags), *args, delta=cu(delta), limits=cu(limits))
+        torch.cuda.synchronize()
+        outs.append({k: v.cpu().numpy() for k, v in o.items()})
+    a, c = outs
+    assert np.array_equal(a["status"], c["status"]) and np.array_equal(a["theta"], c["theta"])
+    ok = c["status"] == 0
+    assert 0.5 * B < ok.sum()
+    d = np.abs(a["U"][ok] - c["U"][ok]).max(axis=(1, 2))
+    assert d.max() <= 1e-5 and np.percentile(d, 99.9) <= 1e-8
+    assert np.abs(a["obj"][ok] - c["obj"][ok]).max() <= 1e-6 * np.abs(c["obj"][ok]).max()
+    assert np.all(np.isnan(a["U"][~ok]))
+    assert L.lib().ldcbf_trim_workspace() == 0
