@@ -122,11 +122,14 @@ __global__ void __launch_bounds__(CL_THREADS) lidar_clusters_kernel(int R, const
     __syncthreads();
     const int P = sP;
 
-    // ---- 2. eps-graph and core points
-    for (int i = t; i < P; i += CL_THREADS) {
-        const double xi = X[i], yi = Y[i];
-        int count = 0;
-        for (int w = 0; w * 32 < P; ++w) {
+    // ---- 2. eps-graph and core points.  Work items are (word w, point i) pairs with i fastest, so that a scan with a
+    // few more than 128 valid readings does not leave 116 threads idle during a second pass over the points, and the
+    // 32 partners of a word are read as broadcasts.
+    {
+        const int Wp = (P + 31) >> 5;
+        for (int item = t; item < Wp * P; item += CL_THREADS) {
+            const int w = item / P, i = item - w * P;
+            const double xi = X[i], yi = Y[i];
             unsigned bits = 0u;
             const int jend = min(32, P - w * 32);
             for (int jj = 0; jj < jend; ++jj) {
@@ -134,11 +137,15 @@ __global__ void __launch_bounds__(CL_THREADS) lidar_clusters_kernel(int R, const
                 if (dx * dx + dy * dy <= eps2) bits |= 1u << jj;
             }
             ADJ[i * W + w] = bits;
-            count += __popc(bits);
         }
-        const bool core = count >= min_samples;
-        LAB[i] = core ? i : CL_BIG;
-        if (core) atomicOr(&CORE[i >> 5], 1u << (i & 31));
+        __syncthreads();
+        for (int i = t; i < P; i += CL_THREADS) {
+            int count = 0;
+            for (int w = 0; w < Wp; ++w) count += __popc(ADJ[i * W + w]);
+            const bool core = count >= min_samples;
+            LAB[i] = core ? i : CL_BIG;
+            if (core) atomicOr(&CORE[i >> 5], 1u << (i & 31));
+        }
     }
     __syncthreads();
 
@@ -157,6 +164,10 @@ __global__ void __launch_bounds__(CL_THREADS) lidar_clusters_kernel(int R, const
                     m = min(m, LAB[j]);
                 }
             }
+            // pointer jumping: the label of my label (labels are indices of core points of the same component and only
+            // ever decrease, so a stale read is still a valid, if larger, candidate) — a chain of k readings in ray
+            // order converges in ~log k sweeps instead of ~k / (neighbours per point)
+            if (m != CL_BIG) { const int m2 = LAB[m]; m = min(m, m2); const int m3 = LAB[m]; m = min(m, m3); }
             if (m < LAB[i]) { LAB[i] = m; sChanged = 1; }
         }
         __syncthreads();
@@ -236,15 +247,27 @@ __global__ void __launch_bounds__(CL_THREADS) lidar_clusters_kernel(int R, const
     __syncthreads();
 
     // ---- 7. one thread per cluster: duplicates out, flatness test, Andrew's monotone chain (concurrently)
+    // Cluster c goes to lane c / 4 of warp c % 4: the first four clusters (a scan has three on average) get a warp
+    // each — threads of one warp would execute their data-dependent hull loops one after the other.
     const int nc = min(n_clusters, CL_MAXC);
-    if (t < nc) {
-        const int s0 = SEG0[t], cnt = SEGN[t] - s0;
+    const int cl = (t & 31) * (CL_THREADS / 32) + (t >> 5);
+    if (cl < nc) {
+        const int s0 = SEG0[cl], cnt = SEGN[cl] - s0;
         double* sx = SX + s0;
         double* sy = SY + s0;
-        int* hull = HULL + s0 + t;               // cnt + 1 entries are enough; regions of different clusters are disjoint
+        int* hull = HULL + s0 + cl;               // cnt + 1 entries are enough; regions of different clusters are disjoint
+        // (this thread works alone while the rest of the block waits at the next barrier — ncu attributed 38 % of the
+        // kernel's stall samples to that wait — so the serial loops below keep what they just touched in registers
+        // instead of re-reading it from shared memory through an index: the top two points of the hull stack, the
+        // last kept point of the duplicate filter)
         int u = 0;
-        for (int i = 0; i < cnt; ++i)
-            if (u == 0 || sx[i] != sx[u - 1] || sy[i] != sy[u - 1]) { sx[u] = sx[i]; sy[u] = sy[i]; ++u; }
+        {
+            double lx = 0.0, ly = 0.0;
+            for (int i = 0; i < cnt; ++i) {
+                const double qx = sx[i], qy = sy[i];
+                if (u == 0 || qx != lx || qy != ly) { sx[u] = qx; sy[u] = qy; lx = qx; ly = qy; ++u; }
+            }
+        }
         int h = 0;
         if (u >= 3) {
             // The reference drops a cluster when np.linalg.matrix_rank(points - points[0]) < 2 (`:75-76`) or when
@@ -254,35 +277,46 @@ __global__ void __launch_bounds__(CL_THREADS) lidar_clusters_kernel(int R, const
             // extremes <= 64 eps max|coordinate|.
             const double dxl = sx[u - 1] - sx[0], dyl = sy[u - 1] - sy[0];
             const double len = sqrt(dxl * dxl + dyl * dyl);
-            double maxdev = 0.0, scale = 0.0;
+            double maxcross = 0.0, scale = 0.0;        // max |cross| = len * max distance: one division, not one per point
             for (int i = 0; i < u; ++i) {
                 const double ex = sx[i] - sx[0], ey = sy[i] - sy[0];
-                maxdev = fmax(maxdev, fabs(dxl * ey - dyl * ex) / len);
+                maxcross = fmax(maxcross, fabs(dxl * ey - dyl * ex));
                 scale = fmax(scale, fmax(fabs(sx[i]), fabs(sy[i])));
             }
+            const double maxdev = maxcross / len;
             if (maxdev > 64.0 * 2.220446049250313e-16 * scale) {
+                // (ax, ay) / (bx, by): coordinates of hull[h-2] / hull[h-1]; a pop reloads only the new hull[h-2]
+                double ax = 0.0, ay = 0.0, bx = 0.0, by = 0.0;
                 for (int i = 0; i < u; ++i) {
+                    const double qx = sx[i], qy = sy[i];
                     while (h >= 2) {
-                        const int a = hull[h - 2], bq = hull[h - 1];
-                        const double cr = (sx[bq] - sx[a]) * (sy[i] - sy[a]) - (sy[bq] - sy[a]) * (sx[i] - sx[a]);
-                        if (cr <= 0.0) --h; else break;
+                        const double cr = (bx - ax) * (qy - ay) - (by - ay) * (qx - ax);
+                        if (cr <= 0.0) {
+                            --h; bx = ax; by = ay;
+                            if (h >= 2) { const int a = hull[h - 2]; ax = sx[a]; ay = sy[a]; }
+                        } else break;
                     }
                     hull[h++] = i;
+                    ax = bx; ay = by; bx = qx; by = qy;
                 }
                 const int lower = h + 1;
                 for (int i = u - 2; i >= 0; --i) {
+                    const double qx = sx[i], qy = sy[i];
                     while (h >= lower) {
-                        const int a = hull[h - 2], bq = hull[h - 1];
-                        const double cr = (sx[bq] - sx[a]) * (sy[i] - sy[a]) - (sy[bq] - sy[a]) * (sx[i] - sx[a]);
-                        if (cr <= 0.0) --h; else break;
+                        const double cr = (bx - ax) * (qy - ay) - (by - ay) * (qx - ax);
+                        if (cr <= 0.0) {
+                            --h; bx = ax; by = ay;
+                            if (h >= 2) { const int a = hull[h - 2]; ax = sx[a]; ay = sy[a]; }
+                        } else break;
                     }
                     hull[h++] = i;
+                    ax = bx; ay = by; bx = qx; by = qy;
                 }
                 --h;                       // the last point repeats the first
                 if (h < 3) h = 0;
             }
         }
-        HN[t] = h;
+        HN[cl] = h;
     }
     __syncthreads();
 
