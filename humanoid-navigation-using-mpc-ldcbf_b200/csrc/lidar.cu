@@ -32,6 +32,28 @@ __global__ void __launch_bounds__(128) lidar_kernel(int R, const double2* __rest
     for (int i = threadIdx.x; i < no * max_verts; i += blockDim.x) sv[i] = gv[i];
     for (int i = threadIdx.x; i < no; i += blockDim.x) snv[i] = min(nverts[(size_t)b * max_obs + i], max_verts);
     __syncthreads();
+    // Obstacles out of reach are dropped for the whole block (their edge count is set to 0): a ray is a segment of
+    // length lidar_range from `pos`, every intersection point lies inside the obstacle's bounding box, so a box farther
+    // away than the range cannot be hit by any ray.  The margin (1e-9 relative against rounding of ~1e-16) keeps the
+    // test conservative; a culled obstacle produces exactly what the edge loop would have: no hit.  Config 3 keeps ~5
+    // of 20 obstacles per scan.
+    {
+        const double2 pc = pos[b];
+        const double reach = lidar_range * (1.0 + 1e-9) + 1e-300;
+        for (int o = threadIdx.x; o < no; o += blockDim.x) {
+            const int n = snv[o];
+            if (n <= 0) continue;
+            const double2* ring = sv + (size_t)o * max_verts;
+            double lox = ring[0].x, hix = lox, loy = ring[0].y, hiy = loy;
+            for (int e = 1; e < n; ++e) {
+                lox = fmin(lox, ring[e].x); hix = fmax(hix, ring[e].x);
+                loy = fmin(loy, ring[e].y); hiy = fmax(hiy, ring[e].y);
+            }
+            const double dx = fmax(fmax(lox - pc.x, pc.x - hix), 0.0), dy = fmax(fmax(loy - pc.y, pc.y - hiy), 0.0);
+            if (dx * dx + dy * dy > reach * reach) snv[o] = 0;
+        }
+    }
+    __syncthreads();
 
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
