@@ -45,13 +45,18 @@ struct ClusterLayout {
         W = RP / 32;
         NS = 32;
         while (NS < RP) NS <<= 1;
+        // The sort buffers (sx, sy, sc) and the eps-graph share one region: sx / sy stage the raw readings in step 1,
+        // before the graph is built (step 2), and are not written again until the graph has been read for the last
+        // time (border points, step 4).  10 KB less per block at R = 360 -> one more resident block per SM.
         size_t o = 0;
         o += sizeof(double) * RP; off_y = o;
         o += sizeof(double) * RP; off_sx = o;
-        o += sizeof(double) * NS; off_sy = o;
-        o += sizeof(double) * NS; off_sc = o;
-        o += sizeof(int) * NS; off_adj = o;
-        o += sizeof(unsigned) * RP * W; off_core = o;
+        const size_t sort_bytes = sizeof(double) * NS * 2 + sizeof(int) * NS;
+        const size_t adj_bytes = sizeof(unsigned) * RP * W;
+        off_sy = off_sx + sizeof(double) * NS;
+        off_sc = off_sy + sizeof(double) * NS;
+        off_adj = off_sx;
+        o += sort_bytes > adj_bytes ? sort_bytes : adj_bytes; off_core = o;
         o += sizeof(unsigned) * W; off_ray = o;
         o += sizeof(int) * RP; off_lab = o;
         o += sizeof(int) * RP; off_cid = o;
