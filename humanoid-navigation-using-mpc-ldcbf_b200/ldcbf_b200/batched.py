@@ -37,6 +37,11 @@ class BatchedHumanoidMPC:
         self._pinned = None
         self._step_graph, self._step_graph_key, self._step_graph_ok = None, None, None
 
+    def _scene_key(self):
+        """Addresses of the scenario tensors a captured graph has baked in (a replaced tensor forces a re-capture)."""
+        return tuple(0 if t is None else t.data_ptr() for t in (self.goal, self.verts, self.nverts, self.nobs,
+                                                                 self.delta, self.limits)) + (self.prm.flags, self.N)
+
     def _dev(self, a, dtype):
         if isinstance(a, torch.Tensor):
             return a.to(device=self.device, dtype=dtype).contiguous()
@@ -55,7 +60,7 @@ class BatchedHumanoidMPC:
             self._out = _b.mpc_step(self.prm, x0, theta0, g, foot, self.verts, self.nverts, self.nobs,
                                     delta=self.delta, limits=self.limits, out=self._out)
             return self._out
-        key = (x0.data_ptr(), theta0.data_ptr(), foot.data_ptr(), g.data_ptr(), tuple(x0.shape))
+        key = (x0.data_ptr(), theta0.data_ptr(), foot.data_ptr(), g.data_ptr(), tuple(x0.shape)) + self._scene_key()
         if self._step_graph_key != key:
             self._out = _b.mpc_step(self.prm, x0, theta0, g, foot, self.verts, self.nverts, self.nobs,
                                     delta=self.delta, limits=self.limits, out=self._out)      # eager once: allocations
@@ -91,7 +96,7 @@ class BatchedHumanoidMPC:
             self._d_state = torch.empty((B, 6), dtype=torch.float64, device=self.device)
             self._packed = None
             self._graph, self._graph_key, self._graph_ok = None, None, B < 148 * 2 * 128 * 4
-        key = (state_host.data_ptr(), tuple(state_host.shape))
+        key = (state_host.data_ptr(), tuple(state_host.shape)) + self._scene_key()
         if self._graph_ok and self._graph_key != key:
             self._enqueue_host_step(state_host)               # eager once: allocations, lazy module loading
             torch.cuda.current_stream().synchronize()
