@@ -209,6 +209,7 @@ def run_ours(args):
     port = CpuPort(os.cpu_count() or 1) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L.lib()
     B, N = args.batch, N_HORIZON
