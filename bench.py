@@ -4,16 +4,22 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one batched MPC step (half-planes K1 + heading/assembly/solve/integrate K2+K3) over the batch of
-BASELINE.json config 2 ("Batched basic simulation: 4096 randomized start/goal poses x 3 obstacles"), one solve per
-scenario, inputs resident in HBM.  Each rank owns its own copy of the 4096 scenarios (weak scaling with equal work per GPU, no data-path collective);
-the time of a step is measured with CUDA events on the launching stream, L2 is flushed between timed steps, and
-the job time is the max over ranks.
+`value` is SURVEY.md §8d's config 2: ONE batch of 4096 x N randomised basic simulations (`scenarios.config2`, seed 0),
+sharded contiguously over the N ranks (`sharding.shard_bounds`, 4096 per GPU, no data-path collective), each run
+CLOSED LOOP to the reference's stop rule (previous objective < 0.05, HumanoidMpc.py:392), to a failed solve
+(:419-429) or to 150 steps; a "step" of the bench is one such pass over the batch (one `ldcbf_rollout_f64` launch per
+rank), and the number reported is (sum of executed MPC steps over all scenarios and ranks) / time, the time of a
+pass measured with CUDA events on the launching stream, L2 flushed between passes, max over ranks.  LDCBF margin
+delta = 1e-6 m on both arms.  After the timed region the per-scenario results are gathered over NCCL
+(`sharding.gather_results`) and that exchange is timed and check-summed separately (`gather`).
 
-Extra keys on the JSON line: `roofline` (dominant kernel, FP64-pipe bound, peak measured live with an FMA-chain
-probe), `roofline_hbm` (half-plane builder vs MEASURED_PEAKS.json), `cpu_baseline` (the numpy oracle port on the
-host cores), `e2e` (host buffers -> H2D -> step -> D2H through BatchedHumanoidMPC.step_host), `p50_step_us`,
-`large_batch` (same step at B = 2^20 where the GPU is full), `clocks`.
+Extra keys on the JSON line: `step0` (the open-loop first step of the same batch: K1 + K2+K3, the number round 1
+reported as `value`), `roofline` (dominant kernel, FP64-pipe bound, peak measured live with an FMA-chain probe),
+`roofline_hbm` (half-plane builder vs MEASURED_PEAKS.json), `cpu_baseline` (the numpy oracle port on the host
+cores; the LiDAR and half-plane blocks carry a `cpu_baseline` of kind "reference": the reference's own functions
+from baseline/_ref), `e2e` (pinned host buffers -> H2D -> closed loops -> D2H through
+BatchedHumanoidMPC.rollout_host), `large_batch` (open-loop step at B = 2^20 where the GPU is full),
+`config4_sharded` (65536-scenario sub-goal rollouts, 8192 per GPU), `per_rank`, `clocks`.
 """
 import argparse
 import json
@@ -32,7 +38,20 @@ import numpy as np  # noqa: E402
 METRIC = "ldcbf_mpc_qp_solves_per_sec"
 UNIT = "solves/s"
 N_HORIZON = 3
-WORKLOAD = "config2: batched basic simulation, 4096 randomized start/goal poses x 3 circle obstacles, N=3, T=0.4"
+MAX_STEPS = 150         # closed loop to the stop rule or 150 steps
+MARGIN = 1e-6           # LDCBF margin of both arms (the clearance an interior-point iterate keeps)
+WORKLOAD = ("config2: batched basic simulation, 4096 randomized start/goal poses x 3 circle obstacles per GPU, N=3, "
+            "T=0.4, closed loop to the 0.05 stop rule / failed solve / 150 steps, executed MPC steps counted")
+BYTES_ROLLOUT_STEP = 832.0 + 64.0   # a closed-loop step re-reads the scenario's rings (L1/L2) + trajectory row if recorded
+FLOP_K1 = 28.0 * 52                 # ~28 flop per edge x 52 edges — the K1 share of a fused loop step
+
+
+def make_config(batch_per_gpu):
+    """The `config` object of the JSON line — identical on both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "batch_per_gpu": batch_per_gpu, "horizon": N_HORIZON, "obstacles": 3,
+            "max_steps": MAX_STEPS, "ldcbf_margin": MARGIN, "seed": 0,
+            "sharding": "one seeded batch of batch_per_gpu x n_gpus scenarios, contiguous shard per rank",
+            "l2": "flushed (256 MB write) between timed passes on the GPU arm"}
 # algorithmic flop model of the fused step kernel at (N, n_obs) = (3, 3), DESIGN.md §6
 FLOP_PER_ITER = 470.0
 FLOP_SETUP = 500.0
@@ -43,17 +62,22 @@ BYTES_STEP = 1232.0     # inputs 984 B + outputs 248 B
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="only the headline, e2e, step0 and the sharded arms")
     return ap.parse_args()
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# CPU legs (oracle port): the only place bench.py executes oracle/
+# CPU legs: the only place bench.py executes oracle/ (the numpy port) and baseline/_ref (the reference's own functions)
 # ---------------------------------------------------------------------------------------------------------------------
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+STUB_DIR = os.path.join(ROOT, "tools", "mpl_stub")
+
+
 def _cpu_init():
     # one BLAS thread per worker process: the port is a scalar loop, oversubscription only slows it down
     try:
@@ -65,12 +89,15 @@ def _cpu_init():
 
 
 def _cpu_worker(job):
+    """Closed loops of the oracle port (oracle.mpc.run_simulation restates HumanoidMpc.py:380-459) -> executed MPC
+    solves (the failed solve that ends a run included, as in the GPU arm's counter, csrc/rollout.cu)."""
     from oracle import mpc
-    states, goals, foots, rings = job
     n = 0
-    for s, g, f, r in zip(states, goals, foots, rings):
-        mpc.mpc_step(s, g, r, [int(v) for v in f], N=N_HORIZON, sampling_time=0.4)
-        n += 1
+    for state, goal, right_first, rings in job:
+        info = {}
+        mpc.run_simulation(goal, rings, state, N_horizon=N_HORIZON, N_mpc_timesteps=MAX_STEPS, sampling_time=0.4,
+                           start_with_right_foot=bool(right_first), delta=MARGIN, info=info)
+        n += info["solves"]
     return n
 
 
@@ -82,10 +109,11 @@ class CpuPort:
         self.cores = cores
         self.pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init)
 
-    def rate(self, sc, foots, n_sample):
-        idx = np.arange(n_sample) % len(sc["state"])
-        jobs = [(sc["state"][c], sc["goal"][c], foots[c], [sc["rings"][i] for i in c])
-                for c in np.array_split(idx, self.cores) if len(c)]
+    def rate(self, sc, first, n_scen):
+        """Closed loops of scenarios first .. first + n_scen - 1 (mod batch) -> (solves/s, solves, wall seconds)."""
+        idx = (first + np.arange(n_scen)) % len(sc["state"])
+        jobs = [[(sc["state"][i], sc["goal"][i], sc["right_first"][i], sc["rings"][i]) for i in c]
+                for c in np.array_split(idx, min(self.cores, n_scen)) if len(c)]
         t0 = time.perf_counter()
         n = sum(self.pool.map(_cpu_worker, jobs))
         wall = time.perf_counter() - t0
@@ -96,25 +124,77 @@ class CpuPort:
         self.pool.join()
 
 
+def _ref_init():
+    """Worker of the reference-function legs: the UNMODIFIED reference package from baseline/_ref behind the matplotlib
+    stand-in (the reference imports matplotlib at module level for its plots)."""
+    sys.path[:0] = [STUB_DIR, REF_DIR]
+    for m in [m for m in sys.modules if m == "HumanoidNavigation" or m.startswith("HumanoidNavigation.")]:
+        del sys.modules[m]
+
+
+def _ref_lidar_worker(job):
+    """compute_lidar_readings (range_finder_wth_polygons_dbscan.py:26-63) on (position, obstacle vertex arrays) pairs."""
+    from HumanoidNavigation.RangeFinder.range_finder_wth_polygons_dbscan import compute_lidar_readings
+    n = 0
+    for pos, obstacles, rng_, res in job:
+        compute_lidar_readings(pos, obstacles, rng_, res)
+        n += 1
+    return n
+
+
+def _ref_halfplane_worker(job):
+    """get_closest_point_and_normal_vector_from_obs (ObstaclesUtils.py:60-109) for every obstacle of every scenario,
+    called as HumanoidMpc.py:311-317 does."""
+    from scipy.spatial import ConvexHull
+    from HumanoidNavigation.Utils.ObstaclesUtils import ObstaclesUtils
+    hulls = {}
+    n = 0
+    for pos, rings, key in job:
+        if key not in hulls:
+            hulls[key] = [ConvexHull(r) for r in rings]
+        for h in hulls[key]:
+            ObstaclesUtils.get_closest_point_and_normal_vector_from_obs(x=pos, polygon=h, unitary_normal_vector=True)
+        n += 1
+    return n
+
+
+def reference_function_rate(worker, items, cores, seconds=6.0):
+    """units/s of one of the reference's own functions, one process per core, on a bounded sample of `items`
+    (repeated until about `seconds` of wall time).  None when baseline/_ref is not there."""
+    if not os.path.isdir(os.path.join(REF_DIR, "HumanoidNavigation")):
+        return None
+    import multiprocessing as mp
+    with mp.get_context("spawn").Pool(cores, initializer=_ref_init) as pool:
+        chunk = [items[i::cores] for i in range(cores)]
+        chunk = [c for c in chunk if c]
+        pool.map(worker, [c[:1] for c in chunk])                 # imports
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            n += sum(pool.map(worker, chunk))
+        wall = time.perf_counter() - t0
+    return {"value": n / wall, "cores": len(chunk), "kind": "reference", "n": n, "wall_s": wall}
+
+
 def run_reference(args):
     """`--impl reference`: the reference's CPU path for this hot path.  CasADi/IPOPT are not installable offline
     (SURVEY.md §8c), so this times the oracle port — a numpy restatement of HumanoidMpc.py:380-455 with an exact
-    QP solve — on all host cores, on the same config/metric."""
+    QP solve — on all host cores, on the same config/metric: closed loops of scenarios of the SAME seeded batch, one
+    scenario per core per "step" (a bounded sample of the 4096 x n_gpus closed loops of a pass)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from ldcbf_b200 import scenarios
     cores = os.cpu_count() or 1
-    sc = scenarios.config2(512, seed=0)
-    foots = scenarios.foot_window(sc["right_first"], 0, N_HORIZON)
-    per_step = 64 * cores      # bounded sample of the 4096-scenario batch per "step"
-    port = CpuPort(cores)
-    for _ in range(min(args.warmup, 2)):
-        port.rate(sc, foots, per_step)
-    t_total, n_total = 0.0, 0
     steps = max(1, min(args.steps, 20))
-    for _ in range(steps):
-        _, n, wall = port.rate(sc, foots, per_step)
+    warm = min(args.warmup, 1)
+    per = 4 * cores                                   # closed loops per "step": four per core
+    sc = scenarios.config2(min(args.batch, per * (steps + warm)), seed=0)    # a prefix of the seed-0 batch
+    port = CpuPort(cores)
+    for w in range(warm):
+        port.rate(sc, w * per, per)
+    t_total, n_total = 0.0, 0
+    for i in range(steps):
+        _, n, wall = port.rate(sc, (warm + i) * per, per)
         t_total += wall
         n_total += n
     port.close()
@@ -122,9 +202,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_total / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch": args.batch, "horizon": N_HORIZON, "obstacles": 3},
+            "config": make_config(args.batch),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{per_step} scenarios of the batch per step x {steps} steps; numpy oracle "
+                             "sample": f"{per} closed loops (scenarios {warm * per}.. of the seed-0 batch, four per "
+                                       f"core) per step x {steps} steps = {n_total} MPC solves; numpy oracle "
                                        "(reference restatement; CasADi/IPOPT unavailable offline)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -196,11 +277,18 @@ def device_inputs(sc, foots, torch, rep=1):
                 nverts=cu(sc["nverts"], torch.int32), nobs=cu(sc["nobs"], torch.int32))
 
 
+def shard_of(sc, lo, hi):
+    out = {}
+    for k, v in sc.items():
+        out[k] = v[lo:hi] if isinstance(v, (np.ndarray, list)) and len(v) == len(sc["state"]) else v
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import ldcbf_b200 as L
-    from ldcbf_b200 import scenarios
+    from ldcbf_b200 import scenarios, sharding
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -212,85 +300,174 @@ def run_ours(args):
         os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L.lib()
-    B, N = args.batch, N_HORIZON
-    # Weak scaling with exactly equal work per GPU: every rank solves its own copy of the same config-2 batch (the
-    # step time of a latency-bound batch is set by its slowest scenario, so different random batches per rank would
-    # measure the luck of the draw, not the scaling).  No data is shared between ranks.
-    sc = scenarios.config2(B, seed=0)
+    Bg, N = args.batch, N_HORIZON
+    B_total = Bg * world
+    # ONE seeded batch for the whole job, contiguous shard per rank; the generator is sequential, so
+    # every rank draws the same B_total scenarios and keeps its slice: no data moves between ranks
+    lo, hi = sharding.shard_bounds(B_total, world, rank)
+    sc = shard_of(scenarios.config2(B_total, seed=0), lo, hi)
+    B = hi - lo
     foots = scenarios.foot_window(sc["right_first"], 0, N)
     d = device_inputs(sc, foots, torch)
     prm = L.default_params(0.4)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
-    out = {}
+    eng = L.BatchedHumanoidMPC(sc["goal"], sc["verts"], sc["nverts"], sc["nobs"], N_horizon=N, sampling_time=0.4,
+                               delta=np.full(B, MARGIN))
+    st0 = torch.as_tensor(sc["state"], dtype=torch.float64).cuda()
+    rf = torch.as_tensor(sc["right_first"].astype(np.int8)).cuda()
+    state = st0.clone()
+    res = {}
 
-    def step():
-        L.mpc_step(prm, d["x0"], d["th"], d["goal"], d["foot"], d["verts"], d["nverts"], d["nobs"], out=out)
+    def closed_loops():
+        res["r"] = eng.rollout(state, rf, MAX_STEPS, record=False)
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
+    def allreduce(x, op):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    W = max(3, args.warmup)
+    for _ in range(W):
+        state.copy_(st0)
+        closed_loops()
+    sync_all()
+    clk = Clocks(local) if rank == 0 else None          # ONE nvidia-smi poller per job, not one per rank
+    if clk:
+        clk.__enter__()
+    sync_all()
+    ts = []
+    for _ in range(args.steps):
+        state.copy_(st0)                                 # untimed: back to the initial states
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        closed_loops()
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    sync_all()
+    r = res["r"]
+    solves_rank = float(r["total_solves"].item())
+    iters_rank = float(r["total_iters"].item())
+    total_ms = allreduce(sum(ts), dist.ReduceOp.MAX if world > 1 else None)
+    solves_job = allreduce(solves_rank, dist.ReduceOp.SUM if world > 1 else None)
+    value = solves_job * args.steps / (total_ms * 1e-3)
+    ends = torch.bincount(r["end_code"], minlength=len(L.binding.END_NAMES)).double()
+    if world > 1:
+        dist.all_reduce(ends)
+    per_rank = torch.tensor([statistics.median(ts), max(ts), sum(ts), solves_rank], dtype=torch.float64, device="cuda")
+    ranks = [torch.empty_like(per_rank) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(ranks, per_rank)
+    else:
+        ranks = [per_rank]
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": make_config(Bg),
+            "value_is": "config 2 closed loop (SURVEY.md 8d): executed MPC steps of all scenarios / time of the pass; "
+                        "round 1 reported the open-loop first step here - that number is now `step0`",
+            "solver": "dual active set (Goldfarb-Idnani) in CoM-position space, fp64, warm-started from the previous "
+                      "step's shifted active set; K1 + K2+K3 fused in one persistent launch per pass (rollout_kernel)",
+            "gpu_launches": args.steps, "solves_per_pass": solves_job, "mean_steps_per_scenario": solves_job / B_total,
+            "iters_mean": iters_rank / max(1.0, solves_rank), "p50_step_us": 1e3 * statistics.median(ts),
+            "p50_solve_step_us": 1e3 * statistics.median(ts) / float(r["steps"].max().item()),
+            "endings": {n: int(v) for n, v in zip(L.binding.END_NAMES, ends.tolist())},
+            "endings_note": "infeasible_future_rows: LDCBF rows of the predicted stages conflict with the kinematic rows "
+                            "(the reference formulation is not recursively feasible; IPOPT raises there too, "
+                            "HumanoidMpc.py:419-429); infeasible_k0_row: current CoM violates a half-plane by > 1e-6",
+            "per_rank": [{"rank": i, "p50_ms": float(t[0]), "max_ms": float(t[1]), "sum_ms": float(t[2]),
+                          "solves_per_pass": float(t[3])} for i, t in enumerate(x.tolist() for x in ranks)]}
+
+    # ---- C1: gather of the fixed-size per-scenario results over NCCL, after the timed region
+    rows = torch.cat((state, r["steps"].double()[:, None], r["status"].double()[:, None],
+                      r["end_code"].double()[:, None]), dim=1).contiguous()
+    if world > 1:
+        for _ in range(2):
+            allrows = sharding.gather_results(rows, B_total)
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        allrows = sharding.gather_results(rows, B_total)
+        e1.record()
+        e1.synchronize()
+        g_ms = allreduce(e0.elapsed_time(e1), dist.ReduceOp.MAX)
+    else:
+        allrows, g_ms = rows, 0.0
+    w = torch.arange(1, allrows.shape[0] + 1, dtype=torch.float64, device="cuda")
+    checksum = float((allrows[:, 5] * w).sum().item())          # step counts weighted by the global scenario index
+    cs_lo = allreduce(checksum, dist.ReduceOp.MIN if world > 1 else None)
+    cs_hi = allreduce(checksum, dist.ReduceOp.MAX if world > 1 else None)
+    line["gather"] = {"collective": "all_gather (NCCL)" if world > 1 else "none (1 rank)", "ms": g_ms,
+                      "bytes_per_rank_in": rows.numel() * 8, "bytes_out": allrows.numel() * 8,
+                      "rows": int(allrows.shape[0]), "checksum": checksum, "checksum_equal_on_all_ranks": cs_lo == cs_hi,
+                      "solves_from_gathered_rows": float(allrows[:, 5].sum().item())}
+
+    # ---- end to end through the public API with host buffers (every rank; max over ranks)
+    e2e_res = e2e(eng, sc, args, torch)
+    e2e_ms = allreduce(e2e_res["ms_total"], dist.ReduceOp.MAX if world > 1 else None)
+    line["e2e"] = {"value": solves_job * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
+                   "h2d_bytes_per_step": e2e_res["h2d"], "d2h_bytes_per_step": e2e_res["d2h"],
+                   "ms_per_step": e2e_ms / args.steps,
+                   "api": "BatchedHumanoidMPC.rollout_host -> ldcbf_rollout_f64 (pinned [B,5] states + [B] first foot in, "
+                          "pinned [B,8] result rows out, stream synchronise, every pass)"}
+
+    # ---- config 4 sharded: ONE batch of 8192 x n_gpus sub-goal scenarios, shard per rank, gather afterwards
+    line["config4_sharded"] = config4_sharded(L, sharding, world, rank, torch, dist, allreduce, sync_all)
+
+    # ---- the open-loop first step of the same batch (round 1's `value`), per rank, max over ranks
+    out = {}
+    step = lambda: L.mpc_step(prm, d["x0"], d["th"], d["goal"], d["foot"], d["verts"], d["nverts"], d["nobs"],
+                              delta=eng.delta, out=out)
+    for _ in range(5):
         step()
     sync_all()
-    with Clocks(local) as clk:
-        sync_all()
-        ts = timed_steps(step, args.steps, flush, torch)
-        sync_all()
-        total_ms = torch.tensor([sum(ts)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-        total_ms = float(total_ms.item())
-        value = B * args.steps * world / (total_ms * 1e-3)
-        iters = out["iters"].double()
-        status = torch.bincount(out["status"], minlength=4).tolist()
+    t0s = timed_steps(step, max(args.steps, 50), flush, torch)
+    sync_all()
+    s0_ms = allreduce(sum(t0s), dist.ReduceOp.MAX if world > 1 else None)
+    iters = out["iters"].double()
+    line["step0"] = {"value": B_total * len(t0s) / (s0_ms * 1e-3), "unit": UNIT, "ms_per_step": s0_ms / len(t0s),
+                     "p50_step_us": 1e3 * statistics.median(t0s), "iters_mean": float(iters.mean().item()),
+                     "status_counts": torch.bincount(out["status"], minlength=4).tolist(), "gpu_launches_per_step": 2,
+                     "what": "one batched open-loop MPC step (K1 + K2+K3) over the rank's 4096 initial states, L2 flushed"}
 
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "batch_per_gpu": B, "horizon": N, "obstacles": 3,
-                           "per_rank_data": "own copy of the same seeded batch on every rank (equal work per GPU)",
-                           "timing": "CUDA events per step, L2 flushed (256 MB write) between timed steps",
-                           "solver": "dual active set (Goldfarb-Idnani) in CoM-position space, fp64; geometric "
-                                     "active-set guess; two racing pivot orders per scenario at this batch size"},
-                "p50_step_us": 1e3 * statistics.median(ts), "gpu_launches": 2 * args.steps,
-                "iters_mean": float(iters.mean().item()), "status_counts": status}
-
-        # ---- end to end through the public API with host buffers (every rank; max over ranks)
-        e2e_res = e2e(L, sc, foots, args, torch)
-        e2e_ms = torch.tensor([e2e_res["ms_total"]], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-        e2e_ms = float(e2e_ms.item())
-        line["e2e"] = {"value": B * args.steps * world / (e2e_ms * 1e-3), "unit": UNIT,
-                       "h2d_bytes_per_step": e2e_res["h2d"], "d2h_bytes_per_step": e2e_res["d2h"],
-                       "ms_per_step": e2e_ms / args.steps,
-                       "api": "BatchedHumanoidMPC.step_host -> ldcbf_mpc_step_packed_f64 (one pinned [B,6] state row in, one [B,10] result row out)"}
-        if rank == 0:
-            # ---- kernel-only timing of the dominant kernel for the roofline (same inputs, L2 flushed)
-            t_qp = timed_steps(lambda: L.mpc_qp(prm, d["x0"], d["th"], d["goal"], d["foot"], out["c_eta"], d["nobs"],
-                                                out=out), min(args.steps, 50), flush, torch)
-            peak_fp64 = max(L.probe_fp64() for _ in range(3))
-            flops = float((iters * FLOP_PER_ITER + FLOP_SETUP).sum().item())
-            ach = flops / (statistics.mean(t_qp) * 1e-3) / 1e12
-            line["roofline"] = {"bound": "fp64", "kernel": "mpc_qp_race_kernel<3,4,16>", "achieved": ach, "peak": peak_fp64,
-                                "unit": "TFLOP/s", "frac": ach / peak_fp64, "traffic": profile_traffic(B),
-                                "kernel_ms": statistics.mean(t_qp),
-                                "peak_source": "FP64 FMA-chain probe measured in this run (MEASURED_PEAKS.json has no fp64 entry)",
-                                "flop_model": f"sum over scenarios of iters*{FLOP_PER_ITER:.0f} + {FLOP_SETUP:.0f} (iters of the "
-                                              "winning path, warm-start rounds counted as iterations; DESIGN.md §6)",
-                                "note": "B=4096 is 512 half-warps on 592 SM sub-partitions: bound by the instruction "
-                                        "latency of the slowest scenario's path (ncu: 3.9 cycles per issued instruction, "
-                                        "1 warp per sub-partition); large_batch shows the solver with the GPU full"}
-            # ---- large batch: the regime where the GPU is full
+    if rank == 0:
+        peak_fp64 = max(L.probe_fp64() for _ in range(3))
+        # dominant kernel of the headline: rollout_kernel (K1 + K2+K3 fused, one thread x 4 lanes per scenario)
+        flops = iters_rank * FLOP_PER_ITER + solves_rank * (FLOP_SETUP + FLOP_K1)
+        k_ms = statistics.mean(ts)
+        ach = flops / (k_ms * 1e-3) / 1e12
+        line["roofline"] = {"bound": "fp64", "kernel": "rollout_kernel<3,4,exact,32,4>", "achieved": ach, "peak": peak_fp64,
+                            "unit": "TFLOP/s", "frac": ach / peak_fp64, "traffic": profile_traffic("rollout"),
+                            "kernel_ms": k_ms,
+                            "peak_source": "FP64 FMA-chain probe measured in this run (MEASURED_PEAKS.json has no fp64 "
+                                           "entry); profiles/ holds the probe's own ncu counters",
+                            "flop_model": f"iterations*{FLOP_PER_ITER:.0f} + solves*({FLOP_SETUP:.0f} + {FLOP_K1:.0f} for the "
+                                          "52 ring edges) (DESIGN.md §6)",
+                            "note": "4096 closed loops are 4096 sequential chains of <= 150 dependent solves: 512 warps on "
+                                    "592 SM sub-partitions, bound by the instruction latency of the longest chain; "
+                                    "large_batch shows the same solver with the GPU full"}
+        # kernel-only timing of the open-loop solve for step0's roofline (same inputs, L2 flushed)
+        t_qp = timed_steps(lambda: L.mpc_qp(prm, d["x0"], d["th"], d["goal"], d["foot"], out["c_eta"], d["nobs"],
+                                            delta=eng.delta, out=out), 50, flush, torch)
+        f0 = float((iters * FLOP_PER_ITER + FLOP_SETUP).sum().item())
+        a0 = f0 / (statistics.mean(t_qp) * 1e-3) / 1e12
+        line["step0"]["roofline"] = {"bound": "fp64", "kernel": "mpc_qp_race_kernel<3,4,16>", "achieved": a0,
+                                     "peak": peak_fp64, "unit": "TFLOP/s", "frac": a0 / peak_fp64,
+                                     "kernel_ms": statistics.mean(t_qp), "traffic": profile_traffic(B)}
+        if world == 1 and not args.no_extras:
             line["large_batch"] = large_batch(L, sc, foots, prm, flush, peak_fp64, torch)
             # the memory-bound kernel of the path against the measured HBM peak (it needs a full GPU to mean anything)
             line["roofline_hbm"] = dict(line["large_batch"]["roofline_hbm"], batch=line["large_batch"]["batch"],
                                         algorithmic_bytes_per_scenario=BYTES_K1)
-            # ---- the other rows of the hot path: closed-loop rollout kernel, LiDAR caster, single-scenario latency
-            line["rollout"] = rollout_bench(L, sc, torch)
-            line["rollout_margin_1e-6"] = rollout_bench(L, sc, torch, delta=1e-6)
+            # the other rows of the hot path
+            line["rollout_margin_0"] = rollout_bench(L, sc, torch, delta=0.0)
+            line["rollout_cold_start"] = rollout_bench(L, sc, torch, delta=MARGIN, cold=True)
             line["lidar"] = lidar_bench(L, flush, peak_fp64, torch)
             line["subgoal_rollout"] = subgoal_rollout_bench(L, torch)
             line["unknown_env"] = unknown_env_bench(L, flush, torch)
@@ -298,22 +475,115 @@ def run_ours(args):
             line["bounds_tuning"] = bounds_tuning_bench(torch)
             line["long_horizon"] = long_horizon_bench(L, torch)
             line["clearance_grid"] = clearance_bench(L, torch)
+    if clk:
+        clk.__exit__()
     if rank == 0:
         line["clocks"] = clk.summary()
         if port is not None:
             cores = port.cores
-            port.rate(sc, foots, cores * 8)                          # warm the workers (imports)
-            r0, _, _ = port.rate(sc, foots, cores * 64)              # calibration
-            n_sample = int(max(cores * 64, min(r0 * 15.0, 2e6)))    # about 15 s of CPU work
-            rate, n, wall = port.rate(sc, foots, n_sample)
+            port.rate(sc, 0, cores)                                   # warm the workers (imports)
+            r0, _, w0 = port.rate(sc, cores, cores)                   # calibration: one closed loop per core
+            n_scen = int(max(cores, min(cores * round(15.0 / max(w0, 1e-3)), 4096)))    # about 15 s of CPU work
+            rate, n, wall = port.rate(sc, 2 * cores, n_scen)
             port.close()
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{n} solves ({wall:.1f} s): the scenarios of the same batch, one MPC step each, repeated; numpy "
-                                              "oracle (reference restatement; CasADi/IPOPT unavailable offline)"}
+                                    "sample": f"{n_scen} closed loops of the same seed-0 batch (scenarios {2 * cores}..) = {n} "
+                                              f"MPC solves in {wall:.1f} s; numpy oracle (reference restatement; CasADi/IPOPT "
+                                              "unavailable offline)"}
+            if not args.no_extras and "lidar" in line:
+                line["lidar"]["cpu_baseline"] = lidar_reference_baseline(cores)
+                line["roofline_hbm"]["cpu_baseline"] = halfplane_reference_baseline(sc, cores)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def config4_sharded(L, sharding, world, rank, torch, dist, allreduce, sync_all, per_gpu=8192, per_goal=300):
+    """BASELINE.json config 4: 8192 x n_gpus sub-goal scenarios (65536 on 8 GPUs) as ONE seeded batch, contiguous shard
+    per rank, sequential sub-goal runs in one rollout launch per rank (HumanoidMPCWithRRT.py:153-181), then the NCCL
+    gather of the per-scenario result rows (timed separately)."""
+    from ldcbf_b200 import scenarios
+    B_total = per_gpu * world
+    lo, hi = sharding.shard_bounds(B_total, world, rank)
+    c4 = shard_of(scenarios.config4(B_total, seed=0), lo, hi)
+    B = hi - lo
+    cu = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).cuda()
+    prm = L.default_params(0.4)
+    goals, v, nv, no = cu(c4["goals"]), cu(c4["verts"]), cu(c4["nverts"], torch.int32), cu(c4["nobs"], torch.int32)
+    rf = cu(c4["right_first"].astype(np.int8), torch.int8)
+    delta = torch.full((B,), MARGIN, dtype=torch.float64, device="cuda")
+    G = goals.shape[1]
+    st0 = cu(c4["state"])
+    state = st0.clone()
+    run = lambda: L.rollout(prm, state, goals, rf, v, nv, no, T=G * 120, N=N_HORIZON, max_steps_per_goal=per_goal,
+                            delta=delta, record=False)
+    for _ in range(2):
+        state.copy_(st0)
+        r = run()
+    sync_all()
+    ts = []
+    for _ in range(3):
+        state.copy_(st0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = run()
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    sync_all()
+    op_max = dist.ReduceOp.MAX if world > 1 else None
+    op_sum = dist.ReduceOp.SUM if world > 1 else None
+    ms = allreduce(statistics.median(ts), op_max)
+    solves = allreduce(float(r["total_solves"].item()), op_sum)
+    reached = allreduce(float((r["goal_steps"][:, -1] > 0).sum().item()), op_sum)
+    rows = torch.cat((state, r["steps"].double()[:, None], r["status"].double()[:, None],
+                      r["goal_steps"].double()), dim=1).contiguous()
+    if world > 1:
+        allrows = sharding.gather_results(rows, B_total)
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        allrows = sharding.gather_results(rows, B_total)
+        e1.record()
+        e1.synchronize()
+        g_ms = allreduce(e0.elapsed_time(e1), op_max)
+    else:
+        allrows, g_ms = rows, 0.0
+    w = torch.arange(1, allrows.shape[0] + 1, dtype=torch.float64, device="cuda")
+    cs = float((allrows[:, 5] * w).sum().item())
+    equal = allreduce(cs, dist.ReduceOp.MIN if world > 1 else None) == allreduce(cs, op_max)
+    return {"batch_total": B_total, "batch_per_gpu": per_gpu, "sub_goals": G, "solves": solves, "ms": ms,
+            "value": solves / (ms * 1e-3), "unit": UNIT, "scenarios_reaching_last_goal": reached,
+            "gather_ms": g_ms, "gather_bytes_out": allrows.numel() * 8, "gather_checksum": cs,
+            "checksum_equal_on_all_ranks": equal}
+
+
+def lidar_reference_baseline(cores, n_scans=64):
+    """The reference's own compute_lidar_readings on config-3 scans (same generator, same shapes), one process per core."""
+    from ldcbf_b200 import scenarios
+    c3 = scenarios.config3(n_scans, seed=0)
+    items = [(tuple(c3["pos"][i]), [np.asarray(r) for r in c3["rings"][c3["map_index"][i]]], 1.5, 360)
+             for i in range(n_scans)]
+    res = reference_function_rate(_ref_lidar_worker, items, cores)
+    if res is None:
+        return {"value": None, "kind": "reference", "note": "baseline/_ref not present on this box"}
+    return {"value": res["value"], "unit": "scans/s", "cores": res["cores"], "kind": "reference",
+            "sample": f"{res['n']} scans of 360 rays x 20 obstacles in {res['wall_s']:.1f} s: the reference's own "
+                      "compute_lidar_readings (range_finder_wth_polygons_dbscan.py:26-63) from baseline/_ref"}
+
+
+def halfplane_reference_baseline(sc, cores, n_scen=512):
+    """The reference's own get_closest_point_and_normal_vector_from_obs on config-2 scenarios (3 obstacles each)."""
+    n_scen = min(n_scen, len(sc["state"]))
+    items = [(sc["state"][i][[0, 2]].copy(), [np.asarray(r) for r in sc["rings"][i]], i) for i in range(n_scen)]
+    res = reference_function_rate(_ref_halfplane_worker, items, cores)
+    if res is None:
+        return {"value": None, "kind": "reference", "note": "baseline/_ref not present on this box"}
+    return {"value": res["value"], "unit": "scenario-steps/s", "cores": res["cores"], "kind": "reference",
+            "sample": f"{res['n']} scenario-steps (3 obstacles, 52 edges) in {res['wall_s']:.1f} s: the reference's own "
+                      "get_closest_point_and_normal_vector_from_obs (ObstaclesUtils.py:60-109) from baseline/_ref; the "
+                      "ConvexHull objects are built once per scenario outside the count"}
 
 
 def profile_traffic(batch):
@@ -361,15 +631,14 @@ def large_batch(L, sc, foots, prm, flush, peak_fp64, torch, B=1 << 20):
                              "peak_source": hbm_src}}
 
 
-def rollout_bench(L, sc, torch, T=150, delta=None):
-    """Config 2 as SURVEY.md §8d states it: closed loop to the 0.05 stop or 150 steps, one kernel launch.
-    `delta` = LDCBF margin (HumanoidMPCCustomLCBF.py:30-31).  With an exact solver an active LDCBF row puts the next
-    CoM exactly on an obstacle edge, where the reference's normal (x-c)/||x-c|| is numerically undefined
-    (ObstaclesUtils.py:98-104) and the run usually ends infeasible; IPOPT's barrier keeps ~1e-6 clearance
-    implicitly, which delta = 1e-6 reproduces."""
+def rollout_bench(L, sc, torch, T=MAX_STEPS, delta=0.0, cold=False):
+    """Variants of the headline pass for comparison (same scenarios, one launch): `delta` = LDCBF margin
+    (HumanoidMPCCustomLCBF.py:30-31; the headline uses 1e-6), `cold` = LDCBF_FLAG_COLD_START (no warm
+    start from the previous step's active set)."""
     B = len(sc["state"])
+    kw = {"flags": L.binding.FLAG_COLD_START} if cold else {}
     eng = L.BatchedHumanoidMPC(sc["goal"], sc["verts"], sc["nverts"], sc["nobs"], N_horizon=N_HORIZON, sampling_time=0.4,
-                               delta=None if delta is None else np.full(B, delta))
+                               delta=np.full(B, delta), **kw)
     rf = torch.as_tensor(sc["right_first"].astype(np.int8)).cuda()
     st0 = torch.as_tensor(sc["state"], dtype=torch.float64).cuda()
     for _ in range(2):
@@ -386,10 +655,11 @@ def rollout_bench(L, sc, torch, T=150, delta=None):
         ts.append(e0.elapsed_time(e1))
     solves = int(r["total_solves"].item())
     ms = statistics.median(ts)
+    ends = torch.bincount(r["end_code"], minlength=len(L.binding.END_NAMES)).tolist()
     return {"batch": B, "max_steps": T, "solves": solves, "ms": ms, "value": solves / (ms * 1e-3), "unit": UNIT,
-            "us_per_step_of_batch": 1e3 * ms / max(1, int(r["steps"].max().item())), "delta": delta or 0.0,
-            "runs_ending_by_stop_rule": int((r["status"] == 0).sum().item()),
-            "runs_ending_infeasible": int((r["status"] == 2).sum().item())}
+            "us_per_step_of_batch": 1e3 * ms / max(1, int(r["steps"].max().item())), "delta": delta, "cold_start": cold,
+            "iters_mean": float(r["total_iters"].item()) / max(1, solves),
+            "endings": dict(zip(L.binding.END_NAMES, ends))}
 
 
 def subgoal_rollout_bench(L, torch, B=8192, per_goal=300):
@@ -590,24 +860,23 @@ def bounds_tuning_bench(torch):
             "best_combination": [float(v) for v in best], "best_res": res}
 
 
-def e2e(L, sc, foots, args, torch):
-    eng = L.BatchedHumanoidMPC(sc["goal"], sc["verts"], sc["nverts"], sc["nobs"], N_horizon=N_HORIZON, sampling_time=0.4)
-    state6 = np.column_stack((sc["state"], foots[:, 0].astype(np.float64)))      # (..., theta, first stance foot)
-    state_h = torch.as_tensor(state6, dtype=torch.float64).pin_memory()
+def e2e(eng, sc, args, torch):
+    """Same closed loops through the public API with HOST buffers: pinned states in, pinned result rows out."""
+    state_h = torch.as_tensor(sc["state"], dtype=torch.float64).pin_memory()
+    rf_h = torch.as_tensor(sc["right_first"].astype(np.int8)).pin_memory()
     for _ in range(3):
-        eng.step_host(state_h)
+        eng.rollout_host(state_h, rf_h, MAX_STEPS)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
-        res = eng.step_host(state_h)
+        res = eng.rollout_host(state_h, rf_h, MAX_STEPS)
     e1.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
-    assert int((res[:, 9] == 0).sum()) > 0
-    return {"ms_total": max(e0.elapsed_time(e1), wall * 1e3), "h2d": eng.h2d_bytes_per_step,
-            "d2h": eng.d2h_bytes_per_step}
+    assert float(res[:, 5].sum()) > 0
+    return {"ms_total": max(e0.elapsed_time(e1), wall * 1e3), "h2d": eng.rollout_h2d_bytes, "d2h": eng.rollout_d2h_bytes}
 
 
 def main():

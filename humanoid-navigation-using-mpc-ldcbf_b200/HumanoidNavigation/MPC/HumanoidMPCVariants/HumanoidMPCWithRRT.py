@@ -61,6 +61,8 @@ class HumanoidMPCWithRRT(HumanoidMPC):
         if sub_goals is None:
             sub_goals = self.plan_sub_goals()
         self.sub_goals = np.asarray(sub_goals, dtype=np.float64)
+        if self.N_horizon > ldcbf_b200.binding.MAX_HORIZON or self._hooks_overridden():
+            return self._run_per_sub_goal() + (initial_animator,)
         from ldcbf_b200.scenarios import pack_rings
         t = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=self._dev)
         goals = np.asarray(sub_goals, dtype=np.float64).reshape(1, -1, 2)
@@ -68,19 +70,39 @@ class HumanoidMPCWithRRT(HumanoidMPC):
         verts, nverts, nobs = pack_rings([[hull_ring(o) for o in self.obstacles]])
         state = t(np.zeros((1, 5)))                                            # start_state = (0,0,0,0,0), :155
         T = G * self.num_inputs
+        # every sub-goal run is a plain HumanoidMPC in the reference (:160-168): same LDCBF margin as the base class
         r = ldcbf_b200.rollout(self._params(), state, t(goals), t([1 if self.start_with_right_foot else 0], torch.int8),
                                t(verts), t(nverts, torch.int32), t(nobs, torch.int32), T=T, N=self.N_horizon,
-                               max_steps_per_goal=self.num_inputs)
+                               max_steps_per_goal=self.num_inputs, delta=t([self._delta()]))
         gs = r["goal_steps"][0].cpu().numpy()
         X = r["traj_X"][0].cpu().numpy().T
         U = r["traj_U"][0].cpu().numpy().T
-        # the reference concatenates the per-run arrays, so the junction state appears twice (:180-181)
-        Xs, Us, s = [], [], 0
+        # the reference concatenates the per-run arrays, so the junction state appears twice (:180-181); a run that
+        # used up num_inputs steps returns X_pred[:, :num_inputs] (:458) and the next run starts from ITS last column,
+        # the state before the last integration (:178) - the kernel restarts from that state too
+        Xs, Us, s, first = [], [], 0, X[:, 0]
         for g in range(G):
             k = int(gs[g])
+            cols = np.concatenate((first[:, None], X[:, s + 1:s + k + 1]), axis=1)
             if k == self.num_inputs:                                           # run exhausted: last column dropped
-                Xs.append(X[:, s:s + k]); Us.append(U[:, s:s + k - 1])
+                Xs.append(cols[:, :k]); Us.append(U[:, s:s + k - 1])
             else:
-                Xs.append(X[:, s:s + k + 1]); Us.append(U[:, s:s + k])
+                Xs.append(cols); Us.append(U[:, s:s + k])
+            first = Xs[-1][:, -1]
             s += k
         return np.concatenate(Xs, axis=1), np.concatenate(Us, axis=1), initial_animator
+
+    def _run_per_sub_goal(self):
+        """The reference's own sequencing (:153-181), one HumanoidMPC per sub-goal: used for horizons the fused rollout
+        does not cover (N > 4) and when a subclass overrides the half-plane hook."""
+        start_state = (0, 0, 0, 0, 0)                                          # :155
+        Xg, Ug = None, None
+        for sg in self.sub_goals:
+            mpc = HumanoidMPC(goal=tuple(sg), obstacles=self.obstacles, N_horizon=self.N_horizon,
+                              N_mpc_timesteps=self.N_simul, sampling_time=self.sampling_time, init_state=start_state,
+                              start_with_right_foot=self.start_with_right_foot, verbosity=self.verbosity)
+            X, U, _ = mpc.run_simulation(fill_animator=False)
+            start_state = tuple(X[:, -1])                                      # :178
+            Xg = X if Xg is None else np.concatenate((Xg, X), axis=1)
+            Ug = U if Ug is None else np.concatenate((Ug, U), axis=1)
+        return Xg, Ug

@@ -112,8 +112,9 @@ class HumanoidMPC:
                        fill_animator: bool = True, initial_animator=None):
         """Returns (X_pred[5,K+1], U_pred[3,K], animator) like the reference (:345-494); animator is passed through
         (plotting is out of scope)."""
-        if (self._hooks_overridden() or len(self.obstacles) > ldcbf_b200.binding.MAX_OBSTACLES
-                or self.N_horizon > ldcbf_b200.binding.MAX_HORIZON):      # long horizons: block-per-scenario step kernel
+        # any number of obstacles runs fused (8 register-resident, the rest streamed); long horizons use the
+        # block-per-scenario step kernel, one launch per MPC timestep
+        if self._hooks_overridden() or self.N_horizon > ldcbf_b200.binding.MAX_HORIZON:
             X_pred, U_pred = self._run_stepwise()
         else:
             X_pred, U_pred = self._run_fused()

@@ -52,6 +52,9 @@ inline StepConst make_const(const ldcbf_params& p) {
 }
 
 void set_last_error(cudaError_t e);
+// Library-owned stream-ordered memory pool of the current device (mpc_step.cu): record hand-off of the large-batch
+// solve, half-plane scratch of rollouts with more than LDCBF_MAX_OBSTACLES obstacles.  nullptr on failure.
+cudaMemPool_t workspace_pool();
 inline int check_launch() {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_last_error(e); return LDCBF_E_LAUNCH; }

@@ -240,7 +240,7 @@ static int launch_qp_coop(const StepConst& C, int B, int max_obs, const StepIO& 
 // after the first one.
 static std::mutex g_pool_mutex;
 static cudaMemPool_t g_pools[64] = {};
-static cudaMemPool_t record_pool() {
+cudaMemPool_t workspace_pool() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
     std::lock_guard<std::mutex> lock(g_pool_mutex);
@@ -375,7 +375,7 @@ static int launch_qp(const StepConst& C, int B, int max_obs, const StepIO& io, c
         constexpr int CHUNK = 1 << 20;
         const int Bmax = B < CHUNK ? B : CHUNK;
         double* rec = nullptr;
-        cudaMemPool_t pool = record_pool();
+        cudaMemPool_t pool = workspace_pool();
         cudaError_t e = pool ? cudaMallocFromPoolAsync(&rec, (size_t)QpRecord<N>::DOUBLES * sizeof(double) * Bmax, pool, st)
                              : cudaErrorMemoryAllocation;
         if (e != cudaSuccess) { set_last_error(e); cudaGetLastError(); return LDCBF_E_LAUNCH; }

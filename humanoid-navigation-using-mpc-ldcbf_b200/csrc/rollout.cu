@@ -22,6 +22,9 @@ struct RolloutIO {
     const int32_t* nobs; const double* delta; const double* limits; double* traj_X; double* traj_U;
     int32_t* steps; int32_t* goal_steps; int32_t* status; unsigned long long* total_solves; bool fast_geometry;
     bool warm_start;
+    // ABI 2: half-planes of the obstacles beyond the MO register-resident ones ([B,max_obs] double4, library-owned
+    // scratch), iteration counter, per-scenario reason the loop ended (LDCBF_END_*)
+    double4* ce_scratch; unsigned long long* total_iters; int32_t* end_code;
 };
 
 // G lanes per scenario (small batches): the kernel time is the slowest scenario's chain of sequential steps, and a
@@ -41,14 +44,18 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
     double px = io.state[5 * (size_t)b], vx = io.state[5 * (size_t)b + 1], py = io.state[5 * (size_t)b + 2],
            vy = io.state[5 * (size_t)b + 3], th = io.state[5 * (size_t)b + 4];
     const bool right_first = io.right_first[b] != 0;
-    const int nb = min(io.nobs[b], MO);
+    const int nt = min(io.nobs[b], max_obs);
+    const int nb = min(nt, MO);
+    double4* ces = io.ce_scratch ? io.ce_scratch + (size_t)b * max_obs : nullptr;   // obstacles MO.. are streamed
+    const int n_stream = ces ? nt - nb : 0;
     const double dl = io.delta ? io.delta[b] : 0.0;
     const Limits lim = load_limits(C, io.limits, (size_t)b);
     double* tX = (io.traj_X && writer) ? io.traj_X + (size_t)b * (T + 1) * 5 : nullptr;
     double* tU = (io.traj_U && writer) ? io.traj_U + (size_t)b * T * 3 : nullptr;
     if (tX) { tX[0] = px; tX[1] = vx; tX[2] = py; tX[3] = vy; tX[4] = th; }
 
-    int gi = 0, kstep = 0, total = 0, solves = 0, last_status = LDCBF_STATUS_SOLVED;
+    int gi = 0, kstep = 0, total = 0, solves = 0, iters_sum = 0, last_status = LDCBF_STATUS_SOLVED;
+    int end_code = LDCBF_END_BUDGET;
     int warm[2 * N];                       // active set of the previous step, shifted by one stage (-1: none)
 #pragma unroll
     for (int j = 0; j < 2 * N; ++j) warm[j] = -1;
@@ -57,6 +64,14 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
 
     while (gi < n_goals && total < T) {
         if (last_obj < C.stop_objective || kstep >= max_steps_per_goal) {     // :392 / loop exhausted
+            end_code = last_obj < C.stop_objective ? LDCBF_END_STOP_RULE : LDCBF_END_BUDGET;
+            if (!(last_obj < C.stop_objective) && gi + 1 < n_goals) {
+                // a run that used up its num_inputs steps returns X_pred[:, :num_inputs] (HumanoidMpc.py:458) and the
+                // next sub-goal run starts from its LAST column (HumanoidMPCWithRRT.py:178): the state before the last
+                // integration, parked in io.state below
+                px = io.state[5 * (size_t)b]; vx = io.state[5 * (size_t)b + 1]; py = io.state[5 * (size_t)b + 2];
+                vy = io.state[5 * (size_t)b + 3]; th = io.state[5 * (size_t)b + 4];
+            }
             if (writer) io.goal_steps[(size_t)b * n_goals + gi] = kstep;
             ++gi; kstep = 0; last_obj = INFINITY;
 #pragma unroll
@@ -65,6 +80,10 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
         }
         const double gx = io.goals[((size_t)b * n_goals + gi) * 2], gy = io.goals[((size_t)b * n_goals + gi) * 2 + 1];
         double th1, om0;
+        if (n_goals > 1 && kstep + 1 >= max_steps_per_goal) {      // last step of a run: park the state before it (lanes
+            io.state[5 * (size_t)b] = px; io.state[5 * (size_t)b + 1] = vx; io.state[5 * (size_t)b + 2] = py;   // of a group
+            io.state[5 * (size_t)b + 3] = vy; io.state[5 * (size_t)b + 4] = th;                  // store equal values)
+        }
         if (kstep % substeps == 0) {
             // half-planes at the current CoM (:387)
             double4 ce[MO];
@@ -78,6 +97,13 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
                                                           glane, gmask);
                 }
             }
+            // every lane of the group stores the same value and later reads back its own store: no synchronisation
+            for (int o = MO; o < MO + n_stream; ++o) {
+                const int V = min(io.nverts[(size_t)b * max_obs + o], max_verts);
+                ces[o] = V > 0 ? halfplane_group<EXACT, G>(px, py, io.verts + ((size_t)b * max_obs + o) * max_verts, V,
+                                                           glane, gmask)
+                               : make_double4(0.0, 0.0, 0.0, 0.0);
+            }
             int ft[N + 1];
             const int step_number = kstep / substeps;                                 // :401
 #pragma unroll
@@ -86,7 +112,7 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
             {
                 QpState<N, MO> qs;
                 double* ws = qp_ws + threadIdx.x;
-                qp_setup<N, MO, BLOCK>(C, px, vx, py, vy, th, gx, gy, ft, ce, nb, nullptr, 0, dl, lim, ws, qs);
+                qp_setup<N, MO, BLOCK>(C, px, vx, py, vy, th, gx, gy, ft, ce, nb, ces ? ces + MO : nullptr, n_stream, dl, lim, ws, qs);
                 if (io.warm_start) {
                     bool any = false;                       // nothing carried over (first step of a run): geometric guess
 #pragma unroll
@@ -99,8 +125,12 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
                 shift_codes<N, MO, BLOCK>(qs, ws, warm);
             }
             solves += writer ? 1 : 0;
+            iters_sum += writer ? S.iters : 0;
             last_status = S.status;
             if (S.status != LDCBF_STATUS_SOLVED) {                                    // :419-429 break
+                end_code = S.status == LDCBF_STATUS_DEGENERATE ? LDCBF_END_DEGENERATE
+                         : S.status == LDCBF_STATUS_MAX_ITER ? LDCBF_END_MAX_ITER
+                         : S.iters == 0 ? LDCBF_END_INFEASIBLE_NOW : LDCBF_END_INFEASIBLE_AHEAD;
                 if (writer) io.goal_steps[(size_t)b * n_goals + gi] = kstep;
                 ++gi; kstep = 0; last_obj = INFINITY;
 #pragma unroll
@@ -133,12 +163,17 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
         io.state[5 * (size_t)b + 3] = vy; io.state[5 * (size_t)b + 4] = th;
         io.steps[b] = total;
         io.status[b] = last_status;
+        if (io.end_code) io.end_code[b] = (gi < n_goals && total >= T) ? LDCBF_END_BUDGET : end_code;
     }
     if (io.total_solves) {
         // one atomic per warp, whatever subset of its lanes is still here (blocks of 8 threads, ragged last block)
         const unsigned m = __activemask();
         const unsigned s = __reduce_add_sync(m, (unsigned)solves);
         if ((threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) atomicAdd(io.total_solves, (unsigned long long)s);
+        if (io.total_iters) {
+            const unsigned it = __reduce_add_sync(m, (unsigned)iters_sum);
+            if ((threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) atomicAdd(io.total_iters, (unsigned long long)it);
+        }
     }
 }
 
@@ -179,8 +214,9 @@ template <int N>
 static int dispatch_rollout(const StepConst& C, int B, int T, int n_goals, int msg, int sub, int max_obs,
                             int max_verts, const RolloutIO& io, cudaStream_t st) {
     if (max_obs <= 4) return launch_rollout<N, 4>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
-    if (max_obs <= LDCBF_MAX_OBSTACLES) return launch_rollout<N, 8>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
-    return LDCBF_E_SHAPE;
+    // up to 8 obstacles are register-resident; further ones are streamed from the scratch the caller of this function
+    // allocated (their half-planes are rebuilt there every step)
+    return launch_rollout<N, 8>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
 }
 
 }  // namespace ldcbf
@@ -190,7 +226,7 @@ extern "C" int ldcbf_rollout_f64(const ldcbf_params* prm, int B, int N, int T, i
                                  const int8_t* right_first, const double* verts, const int32_t* nverts,
                                  const int32_t* nobs, const double* delta, const double* limits, double* traj_X,
                                  double* traj_U, int32_t* steps, int32_t* goal_steps, int32_t* status,
-                                 int64_t* total_solves, void* cuda_stream) {
+                                 int64_t* total_solves, int64_t* total_iters, int32_t* end_code, void* cuda_stream) {
     using namespace ldcbf;
     if (!prm || B < 0 || T <= 0 || n_goals <= 0 || max_steps_per_goal <= 0 || max_obs <= 0 || max_verts <= 0)
         return LDCBF_E_ARG;
@@ -200,16 +236,29 @@ extern "C" int ldcbf_rollout_f64(const ldcbf_params* prm, int B, int N, int T, i
     const StepConst C = make_const(*prm);
     int sub = (int)(prm->delta_t / prm->sampling_time);                      // HumanoidMpc.py:74-75
     if (sub <= 0) sub = 1;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    // more obstacles than the register-resident 8 (the reference's CROWDED maps have 20, simulation_1.py:201-231):
+    // their half-planes go through a stream-ordered scratch from the library's pool, 32 B per (scenario, obstacle)
+    double4* scratch = nullptr;
+    if (max_obs > LDCBF_MAX_OBSTACLES) {
+        cudaMemPool_t pool = workspace_pool();
+        cudaError_t e = pool ? cudaMallocFromPoolAsync(&scratch, sizeof(double4) * (size_t)B * max_obs, pool, st)
+                             : cudaErrorMemoryAllocation;
+        if (e != cudaSuccess) { set_last_error(e); cudaGetLastError(); return LDCBF_E_LAUNCH; }
+    }
     const RolloutIO io{state, goals, right_first, reinterpret_cast<const double2*>(verts), nverts, nobs, delta, limits,
                        traj_X, traj_U, steps, goal_steps, status,
                        reinterpret_cast<unsigned long long*>(total_solves),
-                       (prm->flags & LDCBF_FLAG_FAST_GEOMETRY) != 0, (prm->flags & LDCBF_FLAG_COLD_START) == 0};
-    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+                       (prm->flags & LDCBF_FLAG_FAST_GEOMETRY) != 0, (prm->flags & LDCBF_FLAG_COLD_START) == 0,
+                       scratch, reinterpret_cast<unsigned long long*>(total_iters), end_code};
+    int rc;
     switch (N) {
-        case 1: return dispatch_rollout<1>(C, B, T, n_goals, max_steps_per_goal, sub, max_obs, max_verts, io, st);
-        case 2: return dispatch_rollout<2>(C, B, T, n_goals, max_steps_per_goal, sub, max_obs, max_verts, io, st);
-        case 3: return dispatch_rollout<3>(C, B, T, n_goals, max_steps_per_goal, sub, max_obs, max_verts, io, st);
-        case 4: return dispatch_rollout<4>(C, B, T, n_goals, max_steps_per_goal, sub, max_obs, max_verts, io, st);
-        default: return LDCBF_E_SHAPE;
+        case 1: rc = dispatch_rollout<1>(C, B, T, n_goals, max_steps_per_goal, sub, max_obs, max_verts, io, st); break;
+        case 2: rc = dispatch_rollout<2>(C, B, T, n_goals, max_steps_per_goal, sub, max_obs, max_verts, io, st); break;
+        case 3: rc = dispatch_rollout<3>(C, B, T, n_goals, max_steps_per_goal, sub, max_obs, max_verts, io, st); break;
+        case 4: rc = dispatch_rollout<4>(C, B, T, n_goals, max_steps_per_goal, sub, max_obs, max_verts, io, st); break;
+        default: rc = LDCBF_E_SHAPE;
     }
+    if (scratch) cudaFreeAsync(scratch, st);
+    return rc;
 }

@@ -137,6 +137,34 @@ class BatchedHumanoidMPC:
                           max_steps_per_goal=max_steps_per_goal, delta=self.delta, limits=self.limits, record=record)
 
 
+    def rollout_host(self, state_host, right_first_host, T, goals=None, max_steps_per_goal=None):
+        """End-to-end closed loop: pinned host state[B,5] and right_first[B] (int8) in, one upload, ONE launch for all
+        the steps of all scenarios, one download and a stream synchronise.  Returns the pinned host tensor
+        result[B,8] = (final state[5], executed steps, status of the last solve, LDCBF_END_* code), reused between
+        calls."""
+        B = self.B
+        if getattr(self, "_ro_pinned", None) is None:
+            self._ro_pinned = torch.empty((B, 8), dtype=torch.float64).pin_memory()
+            self._ro_state = torch.empty((B, 5), dtype=torch.float64, device=self.device)
+            self._ro_rf = torch.empty((B,), dtype=torch.int8, device=self.device)
+            self._ro_res = torch.empty((B, 8), dtype=torch.float64, device=self.device)
+        self._ro_state.copy_(state_host, non_blocking=True)
+        self._ro_rf.copy_(right_first_host, non_blocking=True)
+        r = self.rollout(self._ro_state, self._ro_rf, T, goals=goals, max_steps_per_goal=max_steps_per_goal, record=False)
+        res = self._ro_res
+        res[:, :5] = self._ro_state
+        res[:, 5] = r["steps"]
+        res[:, 6] = r["status"]
+        res[:, 7] = r["end_code"]
+        self._ro_pinned.copy_(res, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self._ro_last = r
+        return self._ro_pinned
+
+    rollout_h2d_bytes = property(lambda self: self.B * (5 * 8 + 1))
+    rollout_d2h_bytes = property(lambda self: self.B * 8 * 8)
+
+
 class BatchedUnknownEnvMPC(BatchedHumanoidMPC):
     """Unknown-environment variant, batched and entirely on the device: every step scans the true map with the LiDAR
     caster (K4), clusters the readings and builds the convex hulls (f1), and solves the MPC step against the

@@ -39,6 +39,9 @@ class Status:
     SOLVED, MAX_ITER, INFEASIBLE, DEGENERATE, DONE = range(5)
 
 
+END_NAMES = ("stop_rule", "step_budget", "infeasible_k0_row", "infeasible_future_rows", "degenerate", "iteration_cap")
+
+
 _lib = None
 
 
@@ -64,7 +67,7 @@ def lib():
         L.ldcbf_lidar_cast_f64.argtypes = [c_int, c_int, P, c_double, P, c_int, c_int, P, P, P, P, P, P, P]
         L.ldcbf_lidar_clusters_f64.argtypes = [c_int, c_int, P, P, c_double, c_int, c_int, c_int, P, P, P, P, P, P]
         L.ldcbf_clearance_grid_f64.argtypes = [c_int, c_int, c_int, c_int, c_int] + [P] * 10
-        L.ldcbf_rollout_f64.argtypes = [POINTER(LdcbfParams)] + [c_int] * 7 + [P] * 15
+        L.ldcbf_rollout_f64.argtypes = [POINTER(LdcbfParams)] + [c_int] * 7 + [P] * 17
         L.ldcbf_probe_fp64_fma.argtypes = [c_int, c_int, c_int, P, P]
         for name in EXPORTS:
             getattr(L, name)
@@ -276,7 +279,8 @@ def lidar_clusters(hit_xy, noise=None, eps=0.3, min_samples=3, max_hulls=MAX_OBS
 def rollout(prm, state, goals, right_first, verts, nverts, nobs, T, N=3, max_steps_per_goal=None, delta=None,
             limits=None, record=True):
     """Closed loop in one launch.  state[B,5] is updated in place.  goals[B,n_goals,2].
-    Returns dict(traj_X[B,T+1,5], traj_U[B,T,3], steps[B], goal_steps[B,n_goals], status[B], total_solves)."""
+    Returns dict(traj_X[B,T+1,5], traj_U[B,T,3], steps[B], goal_steps[B,n_goals], status[B], total_solves,
+    total_iters, end_code[B] (END_* below))."""
     B, n_goals = state.shape[0], goals.shape[1]
     dev = state.device
     max_obs, max_verts = verts.shape[1], verts.shape[2]
@@ -286,16 +290,19 @@ def rollout(prm, state, goals, right_first, verts, nverts, nobs, T, N=3, max_ste
     steps = torch.empty((B,), dtype=I32, device=dev)
     goal_steps = torch.empty((B, n_goals), dtype=I32, device=dev)
     status = torch.empty((B,), dtype=I32, device=dev)
-    total = torch.zeros((1,), dtype=I64, device=dev)
+    total = torch.zeros((2,), dtype=I64, device=dev)          # (solves, active-set iterations)
+    end_code = torch.empty((B,), dtype=I32, device=dev)
     _check(lib().ldcbf_rollout_f64(ctypes.byref(prm), B, N, T, n_goals, max_steps_per_goal, max_obs, max_verts,
                                    _ptr(state, F64, "state"), _ptr(goals, F64, "goals"),
                                    _ptr(right_first, I8, "right_first"), _ptr(verts, F64, "verts"),
                                    _ptr(nverts, I32, "nverts"), _ptr(nobs, I32, "nobs"), _ptr(delta, F64, "delta"),
                                    _ptr(limits, F64, "limits"), _ptr(tX, F64, "traj_X"), _ptr(tU, F64, "traj_U"),
                                    _ptr(steps, I32, "steps"), _ptr(goal_steps, I32, "goal_steps"),
-                                   _ptr(status, I32, "status"), _ptr(total, I64, "total_solves"), _stream()),
+                                   _ptr(status, I32, "status"), total.data_ptr(), total.data_ptr() + 8,
+                                   _ptr(end_code, I32, "end_code"), _stream()),
            "ldcbf_rollout_f64")
-    return dict(traj_X=tX, traj_U=tU, steps=steps, goal_steps=goal_steps, status=status, total_solves=total)
+    return dict(traj_X=tX, traj_U=tU, steps=steps, goal_steps=goal_steps, status=status, total_solves=total[:1],
+                total_iters=total[1:], end_code=end_code)
 
 
 def probe_fp64(blocks=148 * 8, threads=256, iters=20000):

@@ -26,7 +26,8 @@
 extern "C" {
 #endif
 
-#define LDCBF_ABI_VERSION 1
+#define LDCBF_ABI_VERSION 2   /* 2: ldcbf_rollout_f64 gained total_iters / end_code and streams obstacles beyond 8;
+                                    ldcbf_rollout_unknown_f64 */
 
 /* return codes */
 #define LDCBF_OK 0
@@ -40,6 +41,14 @@ extern "C" {
 #define LDCBF_STATUS_INFEASIBLE 2   /* reference: IPOPT raises, loop breaks (HumanoidMpc.py:419-429) */
 #define LDCBF_STATUS_DEGENERATE 3   /* CoM exactly on an obstacle edge: ||x-c|| = 0 (ObstaclesUtils.py:104) */
 #define LDCBF_STATUS_DONE 4         /* rollout only: scenario already stopped (objective < stop_objective) */
+
+/* why a closed loop ended (ldcbf_rollout_f64 end_code[b]; with sub-goals: the ending of the last run) */
+#define LDCBF_END_STOP_RULE 0         /* previous objective < stop_objective (HumanoidMpc.py:392) */
+#define LDCBF_END_BUDGET 1            /* num_inputs steps of the run / T steps of the buffers used up */
+#define LDCBF_END_INFEASIBLE_NOW 2    /* a constant k = 0 LDCBF row is violated by more than eps_const_row */
+#define LDCBF_END_INFEASIBLE_AHEAD 3  /* the QP over the future stages is infeasible (LDCBF rows against kinematic rows) */
+#define LDCBF_END_DEGENERATE 4        /* CoM exactly on an obstacle edge */
+#define LDCBF_END_MAX_ITER 5
 
 /* supported shapes: horizon 1..4 by the register-resident solver (one thread per scenario) and 5..48 by the
  * long-horizon solver (one thread block per scenario, iteration cap max_iter * ceil(N / 4)); any number of
@@ -197,12 +206,14 @@ int ldcbf_clearance_grid_f64(int B, int width, int h_cap, int max_obs, int max_v
  *   max_steps_per_goal = num_inputs of one run (mpc_step * N_mpc_timesteps)
  *   traj_X [B,T+1,5] or NULL (row 0 = initial state), traj_U [B,T,3] or NULL (f_x, f_y, omega)
  *   steps [B] out: loop iterations executed; goal_steps [B,n_goals] out: iterations spent on each sub-goal;
- *   status [B] out: status of the last solve; total_solves: optional device counter (+= QP solves). */
+ *   status [B] out: status of the last solve; total_solves, total_iters: optional device counters (+= QP solves,
+ *   += active-set iterations of those solves); end_code [B] out or NULL: LDCBF_END_* of the (last) run. */
 int ldcbf_rollout_f64(const ldcbf_params* prm, int B, int N, int T, int n_goals, int max_steps_per_goal, int max_obs,
                       int max_verts, double* state, const double* goals, const int8_t* right_first,
                       const double* verts, const int32_t* nverts, const int32_t* nobs, const double* delta,
                       const double* limits, double* traj_X, double* traj_U, int32_t* steps, int32_t* goal_steps,
-                      int32_t* status, int64_t* total_solves, void* cuda_stream);
+                      int32_t* status, int64_t* total_solves, int64_t* total_iters, int32_t* end_code,
+                      void* cuda_stream);
 
 /* FP64 FMA-chain probe used by bench.py to measure the FP64 pipe peak on the box (roofline denominator).
  * Launches `blocks` x `threads` threads, each running `iters` x 8 independent FMAs; out[blocks*threads]. */

@@ -51,8 +51,10 @@ def mpc_step(state, goal, obstacles, foot, N=3, sampling_time=None, conf=None, d
 
 
 def run_simulation(goal, obstacles, init_state, N_horizon=3, N_mpc_timesteps=100, sampling_time=1e-3,
-                   start_with_right_foot=True, conf=None, delta=0.0):
-    """Closed loop of `HumanoidMPC.run_simulation` (HumanoidMpc.py:345-459).  Returns X_pred[5,K+1], U_pred[3,K]."""
+                   start_with_right_foot=True, conf=None, delta=0.0, info=None):
+    """Closed loop of `HumanoidMPC.run_simulation` (HumanoidMpc.py:345-459).  Returns X_pred[5,K+1], U_pred[3,K].
+    `info` (optional dict) receives `solves` (MPC solves executed, the failed one included) and `end`
+    ("stop_rule", "step_budget" or "status<k>" of the failed solve)."""
     conf = conf or default_conf()
     mpc_steps = int(conf["DELTA_T"] / sampling_time) or 1                    # :74-75
     num_inputs = mpc_steps * N_mpc_timesteps                                 # :78
@@ -64,15 +66,19 @@ def run_simulation(goal, obstacles, init_state, N_horizon=3, N_mpc_timesteps=100
     u0 = np.zeros(2)
     foot = None
     k = 0
+    solves, end = 0, "step_budget"
     for k in range(num_inputs):
         is_mpc = k % mpc_steps == 0
         if last_obj < STOP_OBJECTIVE:                                        # :392
+            end = "stop_rule"
             break
         if is_mpc:
             step_number = k // mpc_steps
             foot = s_v[step_number:step_number + N_horizon + 1]             # :401-403
             r = mpc_step(X_pred[:, k], goal, obstacles, foot, N_horizon, sampling_time, conf, delta)
+            solves += 1
             if r["status"] != 0:                                             # :419-429
+                end = f"status{r['status']}"
                 break
             last_obj = r["obj"]
             u0 = r["U"][0]
@@ -88,6 +94,8 @@ def run_simulation(goal, obstacles, init_state, N_horizon=3, N_mpc_timesteps=100
         else:
             X_pred[:4, k + 1] = X_pred[:4, k]                                # :446
         X_pred[4, k + 1] = theta[1]                                          # :447
+    if info is not None:
+        info.update(solves=solves, end=end)
     return X_pred[:, :k + 1], U_pred[:, :k]                                  # :458-459
 
 

@@ -48,7 +48,7 @@ def test_params_default_match_reference_config(lib):
     assert p.omega_max == conf["OMEGA_MAX"] and p.omega_min == conf["OMEGA_MIN"]
     assert p.foot_offset == model.FOOT_LATERAL_OFFSET and p.stop_objective == model.STOP_OBJECTIVE
     assert p.sampling_time == 1e-3          # ctor default, HumanoidMpc.py:50
-    assert ldcbf_b200.abi_version() == 1
+    assert ldcbf_b200.abi_version() == 2
 
 
 def test_argument_errors_without_device(lib):
@@ -69,7 +69,7 @@ def test_argument_errors_without_device(lib):
     assert lib.ldcbf_mpc_step_f64(ctypes.byref(p), 0, 3, 3, 24, *([None] * 19)) == 0
     assert lib.ldcbf_mpc_step_packed_f64(ctypes.byref(p), 4, 3, 3, 24, *([None] * 11)) == -1
     assert lib.ldcbf_lidar_cast_f64(1, 0, None, 1.5, None, 3, 24, None, None, None, None, None, None, None) == -1
-    assert lib.ldcbf_rollout_f64(ctypes.byref(p), 1, 3, 0, 1, 10, 3, 24, *([None] * 15)) == -1
+    assert lib.ldcbf_rollout_f64(ctypes.byref(p), 1, 3, 0, 1, 10, 3, 24, *([None] * 17)) == -1
     assert lib.ldcbf_workspace_bytes(4096, 3, 3, 24) == 0
 
 
