@@ -100,12 +100,12 @@ def run_simulation(goal, obstacles, init_state, N_horizon=3, N_mpc_timesteps=100
 
 
 def run_subgoals(sub_goals, obstacles, N_horizon=3, N_mpc_timesteps=100, sampling_time=1e-3,
-                 start_with_right_foot=True, conf=None, start_state=(0, 0, 0, 0, 0)):
+                 start_with_right_foot=True, conf=None, start_state=(0, 0, 0, 0, 0), delta=0.0):
     """Sequential fresh runs per sub-goal with state carry-over (HumanoidMPCWithRRT.py:153-181)."""
     Xg, Ug = None, None
     for sg in sub_goals:
         X, U = run_simulation(sg, obstacles, start_state, N_horizon, N_mpc_timesteps, sampling_time,
-                              start_with_right_foot, conf)
+                              start_with_right_foot, conf, delta)
         start_state = tuple(X[:, -1])                                        # :178
         Xg = X if Xg is None else np.concatenate((Xg, X), axis=1)
         Ug = U if Ug is None else np.concatenate((Ug, U), axis=1)

@@ -150,9 +150,57 @@ def test_subgoal_sequencing_matches_oracle():
         s0 = e + 1
 
 
-def test_known_crowded_map_runs_stepwise_with_twenty_obstacles():
-    """The reference's CROWDED map (20 obstacles) as a known map: more obstacles than the rollout kernel holds, so the
-    mirror class runs its stepwise loop (one K1 + one K2+K3 launch per step)."""
+def test_rrt_variant_on_maze2_and_single_subgoal_equals_base_class():
+    """MAZE_2 has 9 obstacles (simulation_maze.py runs HumanoidMPCWithRRT on it with N_horizon = 2): one more than the
+    register-resident 8, so the fused rollout streams the ninth.  And a run with a single sub-goal is exactly the base
+    class's run to that goal (same LDCBF margin, same start)."""
+    from HumanoidNavigation.MPC.HumanoidMpc import HumanoidMPC
+    from HumanoidNavigation.MPC.HumanoidMPCVariants.HumanoidMPCWithRRT import HumanoidMPCWithRRT
+    from HumanoidNavigation.report_simulations.Scenario import FIXED_MAPS
+    from scipy.spatial import ConvexHull
+    hulls = [ConvexHull(np.array(v, dtype=float)) for v in FIXED_MAPS["MAZE_2"]]
+    assert len(hulls) == 9
+    rings = [h.points[h.vertices] for h in hulls]
+    subs = [(2.0, 1.2), (4.5, 1.5), (7.0, 2.0)]
+    m = HumanoidMPCWithRRT(goal=subs[-1], obstacles=hulls, N_horizon=2, N_mpc_timesteps=60, sampling_time=0.4, verbosity=0)
+    X, U, _ = m.run_simulation(None, make_fast_plot=False, fill_animator=False, sub_goals=subs)
+    assert U.shape[1] >= 10 and X.shape[1] == U.shape[1] + len(subs)
+    # first run, transition by transition (horizon 2)
+    cut = next(k for k in range(X.shape[1] - 1) if np.array_equal(X[:, k], X[:, k + 1]))
+    s_v = model.foot_parity(cut + 8, True)
+    from HumanoidNavigation.MPC.HumanoidMpc import INTERIOR_MARGIN
+    for k in range(cut):
+        r = mpc.mpc_step(X[:, k], subs[0], rings, s_v[k:k + 3], N=2, sampling_time=0.4, delta=INTERIOR_MARGIN)
+        assert r["status"] == 0 and np.abs(r["x_next"] - X[:, k + 1]).max() <= 1e-4, k
+    # one sub-goal == the base class
+    wall = ConvexHull(np.array([[2, -3], [2, 3], [3, -3], [3, 3.0]]))
+    a = HumanoidMPCWithRRT(goal=(1.0, 2.0), obstacles=[wall], N_horizon=3, N_mpc_timesteps=60, sampling_time=0.4, verbosity=0)
+    Xa, Ua, _ = a.run_simulation(None, make_fast_plot=False, fill_animator=False, sub_goals=[(1.0, 2.0)])
+    b = HumanoidMPC(goal=(1.0, 2.0), obstacles=[wall], N_horizon=3, N_mpc_timesteps=60, sampling_time=0.4,
+                    init_state=(0, 0, 0, 0, 0), verbosity=0)
+    Xb, Ub, _ = b.run_simulation(None, make_fast_plot=False, fill_animator=False)
+    assert np.array_equal(Xa, Xb) and np.array_equal(Ua, Ub)
+
+
+def test_exhausted_subgoal_run_restarts_from_its_last_returned_state():
+    """A sub-goal run that uses up its num_inputs steps returns X_pred[:, :num_inputs] (HumanoidMpc.py:458) and the next
+    run starts from that array's last column (HumanoidMPCWithRRT.py:178): the oracle's run_subgoals does the same."""
+    from HumanoidNavigation.MPC.HumanoidMPCVariants.HumanoidMPCWithRRT import HumanoidMPCWithRRT
+    from HumanoidNavigation.MPC.HumanoidMpc import INTERIOR_MARGIN
+    subs = [(3.0, 0.5), (3.0, -2.0)]
+    m = HumanoidMPCWithRRT(goal=subs[-1], obstacles=[], N_horizon=3, N_mpc_timesteps=6, sampling_time=0.4, verbosity=0)
+    X, U, _ = m.run_simulation(None, make_fast_plot=False, fill_animator=False, sub_goals=subs)
+    # first run: 6 steps used up -> 6 columns (the 7th is dropped), 5 inputs; second run starts from column 5
+    assert np.array_equal(X[:, 5], X[:, 6])
+    Xo, Uo = mpc.run_subgoals(subs, [], 3, 6, 0.4, True)
+    assert Xo.shape == X.shape and Uo.shape == U.shape
+    np.testing.assert_allclose(X, Xo, atol=1e-6)
+    np.testing.assert_allclose(U, Uo, atol=1e-6)
+
+
+def test_known_crowded_map_runs_fused_with_twenty_obstacles():
+    """The reference's CROWDED map (20 obstacles) as a known map: 8 half-planes register-resident, 12 streamed, the
+    whole loop in one launch."""
     from HumanoidNavigation.MPC.HumanoidMPCVariants.HumanoidMPCCustomLCBF import HumanoidMPCCustomLCBF
     from scipy.spatial import ConvexHull
     geo = helpers.load_geo()
