@@ -471,6 +471,7 @@ def run_ours(args):
             line["lidar"] = lidar_bench(L, flush, peak_fp64, torch)
             line["subgoal_rollout"] = subgoal_rollout_bench(L, torch)
             line["unknown_env"] = unknown_env_bench(L, flush, torch)
+            line["unknown_env_rollout"] = unknown_env_rollout_bench(L, torch)
             line["latency_b1"] = latency_b1(L, torch)
             line["bounds_tuning"] = bounds_tuning_bench(torch)
             line["long_horizon"] = long_horizon_bench(L, torch)
@@ -750,6 +751,38 @@ def unknown_env_bench(L, flush, torch, B=16384):
             "mean_inferred_obstacles": float(out["sensed"]["nobs"].double().mean().item()),
             "overflow": int(out["sensed"]["overflow"].sum().item()),
             "status_counts": torch.bincount(out["status"], minlength=4).tolist(), "gpu_launches_per_step": 4}
+
+
+def unknown_env_rollout_bench(L, torch, B=16384, T=60):
+    """Config 3 as a closed loop on the device (`ldcbf_rollout_unknown_f64`): every step K4 -> f1 -> K1 -> K2+K3 ->
+    advance for all scenarios, no host round trip; starts jittered around the reference's (0, 0, pi/2), noisy readings."""
+    from ldcbf_b200 import scenarios
+    c3 = scenarios.config3(B, seed=0)
+    rs = np.random.default_rng(0)
+    st0 = np.zeros((B, 5))
+    st0[:, 0], st0[:, 2], st0[:, 4] = rs.uniform(-0.2, 0.2, B), rs.uniform(-0.2, 0.2, B), np.pi / 2
+    eng = L.BatchedUnknownEnvMPC(c3["goal"], c3["verts"], c3["nverts"], c3["nobs"], lidar_range=1.5, sampling_time=0.4,
+                                 N_horizon=N_HORIZON, delta=np.full(B, MARGIN))
+    cu = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).cuda()
+    state0, rf = cu(st0, torch.float64), cu(np.ones(B, np.int8), torch.int8)
+    noise = torch.randn((B, 360, 2), dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(0)) * 0.01
+    r = eng.rollout(state0.clone(), rf, T, noise=noise, record=False)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(3):
+        st = state0.clone()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = eng.rollout(st, rf, T, noise=noise, record=False)
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = statistics.median(ts)
+    solves = int(r["total_solves"].item())
+    ends = torch.bincount(r["end_code"], minlength=len(L.binding.END_NAMES)).tolist()
+    return {"batch": B, "max_steps": T, "solves": solves, "ms": ms, "value": solves / (ms * 1e-3), "unit": UNIT,
+            "ms_per_step_of_batch": ms / T, "gpu_launches_per_step": 5, "mean_steps": float(r["steps"].double().mean().item()),
+            "endings": dict(zip(L.binding.END_NAMES, ends))}
 
 
 def latency_b1(L, torch, n=200):

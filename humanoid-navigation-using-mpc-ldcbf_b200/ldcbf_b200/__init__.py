@@ -5,8 +5,8 @@ requires CUDA tensors.  Build with `python __graft_entry__.py build` (or `make -
 """
 from .binding import (LdcbfParams, Status, abi_version, clearance_grid, default_params, half_planes, lib, lidar_cast,
                       lidar_clusters, mpc_qp,
-                      mpc_step, mpc_step_packed, params_from_conf, probe_fp64, rollout)
+                      mpc_step, mpc_step_packed, params_from_conf, probe_fp64, rollout, rollout_unknown)
 from .batched import BatchedHumanoidMPC, BatchedUnknownEnvMPC
 
 __all__ = ["LdcbfParams", "Status", "abi_version", "clearance_grid", "default_params", "half_planes", "lib", "lidar_cast", "lidar_clusters", "mpc_qp",
-           "mpc_step", "mpc_step_packed", "params_from_conf", "probe_fp64", "rollout", "BatchedHumanoidMPC", "BatchedUnknownEnvMPC"]
+           "mpc_step", "mpc_step_packed", "params_from_conf", "probe_fp64", "rollout", "rollout_unknown", "BatchedHumanoidMPC", "BatchedUnknownEnvMPC"]

@@ -40,7 +40,7 @@ class BatchedHumanoidMPC:
     def _scene_key(self):
         """Addresses of the scenario tensors a captured graph has baked in (a replaced tensor forces a re-capture)."""
         return tuple(0 if t is None else t.data_ptr() for t in (self.goal, self.verts, self.nverts, self.nobs,
-                                                                 self.delta, self.limits)) + (self.prm.flags, self.N)
+                                                                 self.delta, self.limits)) + (bytes(self.prm), self.N)
 
     def _dev(self, a, dtype):
         if isinstance(a, torch.Tensor):
@@ -179,6 +179,7 @@ class BatchedUnknownEnvMPC(BatchedHumanoidMPC):
         self.rays = _b.ray_table(lidar_range, lidar_resolution).to(self.device)
         self.max_hulls, self.max_hull_verts = max_hulls, max_hull_verts
         self.eps, self.min_samples = eps, min_samples
+        self.check_overflow = True
 
     def sense(self, pos, noise=None):
         """pos[B,2] -> dict(hit_obs, hit_edge, hit_xy, labels, verts, nverts, nobs, overflow) (inferred obstacles)."""
@@ -189,10 +190,29 @@ class BatchedUnknownEnvMPC(BatchedHumanoidMPC):
         return cl
 
     def step(self, x0, theta0, foot, goal=None, noise=None):
+        """One step for all scenarios.  Raises when a scan produced more hulls / hull vertices than max_hulls /
+        max_hull_verts hold (the reference constrains against EVERY inferred obstacle): rebuild the engine with larger
+        capacities.  The check reads one flag back from the device; `check_overflow=False` on the instance skips it."""
         pos = x0[:, [0, 2]].contiguous()
         sensed = self.sense(pos, noise)
+        if self.check_overflow and bool(sensed["overflow"].any()):
+            raise RuntimeError(f"LiDAR clustering overflow: more than max_hulls={self.max_hulls} hulls or "
+                               f"max_hull_verts={self.max_hull_verts} vertices in a scan; raise the capacities")
         self._out = _b.mpc_step(self.prm, x0, theta0, self.goal if goal is None else goal, foot, sensed["verts"],
                                 sensed["nverts"], sensed["nobs"], delta=self.delta, limits=self.limits, out=self._out)
         out = dict(self._out)
         out["sensed"] = sensed
         return out
+
+    def rollout(self, state, right_first, T, noise=None, record=True):
+        """Closed loop of the variant for all scenarios, entirely on the device (`ldcbf_rollout_unknown_f64`): every step
+        scans the true map from the current CoM, infers the obstacles and solves against them.  state[B,5] CUDA,
+        updated in place; `noise` [B,R,2] is added to the readings of every step.  Raises on clustering overflow."""
+        r = _b.rollout_unknown(self.prm, state, self.goal, right_first, self.verts, self.nverts, self.nobs, T, self.rays,
+                               self.lidar_range, N=self.N, noise=noise, eps=self.eps, min_samples=self.min_samples,
+                               max_hulls=self.max_hulls, max_hull_verts=self.max_hull_verts, delta=self.delta,
+                               limits=self.limits, record=record)
+        if self.check_overflow and bool(r["overflow"].any()):
+            raise RuntimeError(f"LiDAR clustering overflow during the rollout (max_hulls={self.max_hulls}, "
+                               f"max_hull_verts={self.max_hull_verts}); raise the capacities")
+        return r

@@ -18,7 +18,7 @@ EXPORTS = ("ldcbf_abi_version", "ldcbf_params_default", "ldcbf_last_cuda_error",
            "ldcbf_halfplanes_f64", "ldcbf_mpc_qp_f64", "ldcbf_mpc_step_f64", "ldcbf_mpc_step_packed_f64",
            "ldcbf_lidar_cast_f64",
            "ldcbf_lidar_clusters_f64", "ldcbf_clearance_grid_f64",
-           "ldcbf_rollout_f64", "ldcbf_probe_fp64_fma")
+           "ldcbf_rollout_f64", "ldcbf_rollout_unknown_f64", "ldcbf_probe_fp64_fma")
 
 
 class LdcbfParams(ctypes.Structure):
@@ -68,6 +68,8 @@ def lib():
         L.ldcbf_lidar_clusters_f64.argtypes = [c_int, c_int, P, P, c_double, c_int, c_int, c_int, P, P, P, P, P, P]
         L.ldcbf_clearance_grid_f64.argtypes = [c_int, c_int, c_int, c_int, c_int] + [P] * 10
         L.ldcbf_rollout_f64.argtypes = [POINTER(LdcbfParams)] + [c_int] * 7 + [P] * 17
+        L.ldcbf_rollout_unknown_f64.argtypes = ([POINTER(LdcbfParams)] + [c_int] * 4 + [P, c_double, c_int, c_int] + [P] * 7
+                                                + [c_double, c_int, c_int, c_int] + [P] * 10)
         L.ldcbf_probe_fp64_fma.argtypes = [c_int, c_int, c_int, P, P]
         for name in EXPORTS:
             getattr(L, name)
@@ -303,6 +305,33 @@ def rollout(prm, state, goals, right_first, verts, nverts, nobs, T, N=3, max_ste
            "ldcbf_rollout_f64")
     return dict(traj_X=tX, traj_U=tU, steps=steps, goal_steps=goal_steps, status=status, total_solves=total[:1],
                 total_iters=total[1:], end_code=end_code)
+
+
+def rollout_unknown(prm, state, goal, right_first, verts, nverts, nobs, T, rays, lidar_range, N=3, noise=None, eps=0.3,
+                    min_samples=3, max_hulls=MAX_OBSTACLES, max_hull_verts=64, delta=None, limits=None, record=True):
+    """Closed loop of the unknown-environment variant in one call (K4 -> f1 -> K1 -> K2+K3 -> advance per step, all on
+    the device).  state[B,5] is updated in place.  Returns dict(traj_X, traj_U, steps, status, end_code, overflow,
+    total_solves)."""
+    B, dev = state.shape[0], state.device
+    max_obs, max_verts, R = verts.shape[1], verts.shape[2], rays.shape[0]
+    tX = torch.zeros((B, T + 1, 5), dtype=F64, device=dev) if record else None
+    tU = torch.zeros((B, T, 3), dtype=F64, device=dev) if record else None
+    steps = torch.empty((B,), dtype=I32, device=dev)
+    status = torch.empty((B,), dtype=I32, device=dev)
+    end_code = torch.empty((B,), dtype=I32, device=dev)
+    overflow = torch.empty((B,), dtype=I32, device=dev)
+    total = torch.zeros((1,), dtype=I64, device=dev)
+    _check(lib().ldcbf_rollout_unknown_f64(ctypes.byref(prm), B, int(N), int(T), R, _ptr(rays, F64, "rays"),
+                                           float(lidar_range), max_obs, max_verts, _ptr(state, F64, "state"),
+                                           _ptr(goal, F64, "goal"), _ptr(right_first, I8, "right_first"),
+                                           _ptr(verts, F64, "verts"), _ptr(nverts, I32, "nverts"), _ptr(nobs, I32, "nobs"),
+                                           _ptr(noise, F64, "noise"), float(eps), int(min_samples), int(max_hulls),
+                                           int(max_hull_verts), _ptr(delta, F64, "delta"), _ptr(limits, F64, "limits"),
+                                           _ptr(tX, F64, "traj_X"), _ptr(tU, F64, "traj_U"), _ptr(steps, I32, "steps"),
+                                           _ptr(status, I32, "status"), _ptr(end_code, I32, "end_code"),
+                                           _ptr(overflow, I32, "overflow"), _ptr(total, I64, "total_solves"), _stream()),
+           "ldcbf_rollout_unknown_f64")
+    return dict(traj_X=tX, traj_U=tU, steps=steps, status=status, end_code=end_code, overflow=overflow, total_solves=total)
 
 
 def probe_fp64(blocks=148 * 8, threads=256, iters=20000):

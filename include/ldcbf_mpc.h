@@ -215,6 +215,26 @@ int ldcbf_rollout_f64(const ldcbf_params* prm, int B, int N, int T, int n_goals,
                       int32_t* status, int64_t* total_solves, int64_t* total_iters, int32_t* end_code,
                       void* cuda_stream);
 
+/* Closed loop of the unknown-environment variant (HumanoidMPCVariants/HumanoidMPCUnknownEnvironment.py:30-68 inside the
+ * step loop HumanoidMpc.py:380-459): every step scans the TRUE map (verts/nverts/nobs in ConvexHull.points order, as
+ * ldcbf_lidar_cast_f64) from the current CoM, clusters the readings and builds the hulls (as ldcbf_lidar_clusters_f64:
+ * noise [B,R,2] or NULL is added to the readings of every step, eps / min_samples / max_hulls / max_hull_verts as
+ * there) and solves the MPC step against the INFERRED obstacles; stop rule, break on a failed solve, integration and
+ * the alternating foot-parity window as in the reference's loop.  5 launches per step on the caller's stream, no host
+ * round trip; sampling_time must equal delta_t (no sub-stepping, else LDCBF_E_SHAPE).  Work buffers (about
+ * 28*R + 16*max_hulls*max_hull_verts bytes per scenario) come from the library's stream-ordered pool.
+ *   state [B,5] in/out; goal [B,2]; right_first [B] int8
+ *   traj_X [B,T+1,5] or NULL, traj_U [B,T,3] or NULL; steps, status, end_code [B] out (LDCBF_END_*);
+ *   overflow [B] out or NULL: 1 when a scan produced more hulls / hull vertices than max_hulls / max_hull_verts hold
+ *   (the surplus was dropped); total_solves: optional device counter. */
+int ldcbf_rollout_unknown_f64(const ldcbf_params* prm, int B, int N, int T, int R, const double* ray_dirs,
+                              double lidar_range, int max_obs, int max_verts, double* state, const double* goal,
+                              const int8_t* right_first, const double* verts, const int32_t* nverts,
+                              const int32_t* nobs, const double* noise, double eps, int min_samples, int max_hulls,
+                              int max_hull_verts, const double* delta, const double* limits, double* traj_X,
+                              double* traj_U, int32_t* steps, int32_t* status, int32_t* end_code, int32_t* overflow,
+                              int64_t* total_solves, void* cuda_stream);
+
 /* FP64 FMA-chain probe used by bench.py to measure the FP64 pipe peak on the box (roofline denominator).
  * Launches `blocks` x `threads` threads, each running `iters` x 8 independent FMAs; out[blocks*threads]. */
 int ldcbf_probe_fp64_fma(int blocks, int threads, int iters, double* out, void* cuda_stream);
