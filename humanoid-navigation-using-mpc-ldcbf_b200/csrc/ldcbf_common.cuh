@@ -21,7 +21,7 @@ struct StepConst {
     double legx_mid, legx_half, legy_mid, legy_half, vlat_mid, vlat_half;   // two-sided rows as mid +- half
     double omega_max, omega_min;
     double foot_offset, stop_objective, sampling_time;
-    double eps_active, eps_const_row;
+    double eps_active, eps_const_row, eps_infeasible;
     int max_iter;
     bool cold_start;      // LDCBF_FLAG_COLD_START: no initial active-set guess / no warm start
     bool coop_lanes;      // LDCBF_FLAG_COOP_LANES: warp-per-scenario solver for small batches (N <= 3, <= 8 obstacles)
@@ -44,7 +44,7 @@ inline StepConst make_const(const ldcbf_params& p) {
     c.vlat_mid = 0.5 * (p.v_max[1] + p.v_min[1]); c.vlat_half = 0.5 * (p.v_max[1] - p.v_min[1]);
     c.omega_max = p.omega_max; c.omega_min = p.omega_min;
     c.foot_offset = p.foot_offset; c.stop_objective = p.stop_objective; c.sampling_time = p.sampling_time;
-    c.eps_active = p.eps_active; c.eps_const_row = p.eps_const_row;
+    c.eps_active = p.eps_active; c.eps_const_row = p.eps_const_row; c.eps_infeasible = p.eps_infeasible;
     c.max_iter = p.max_iter;
     c.cold_start = (p.flags & LDCBF_FLAG_COLD_START) != 0;
     c.coop_lanes = (p.flags & LDCBF_FLAG_COOP_LANES) != 0;

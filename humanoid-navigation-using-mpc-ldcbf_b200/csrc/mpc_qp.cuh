@@ -185,6 +185,7 @@ struct QpState {
     int p_code;                           // ... and its row code 2*id + (upper side)
     unsigned amask;                       // occupied slots
     int pref;                             // pivot preference of the scan: -1 none, 0 leg rows first, 1 velocity rows first
+    double tol;                           // a row counts as violated below -tol: eps_active, eps_infeasible after a relaxed restart
     int status, iters;
     bool need_scan, done;
 };
@@ -274,6 +275,7 @@ LDCBF_HD void qp_setup(const StepConst& C, double p0x, double v0x, double p0y, d
     for (int k = 1; k <= N; ++k) { s.px[k] = gx; s.py[k] = gy; }
     s.amask = 0;
     s.pref = -1;
+    s.tol = C.eps_active;
     // AN(j, .): signed normal of slot j (zero when free);  GM(i, j): Gram matrix of the slots (identity on free slots)
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
@@ -405,7 +407,7 @@ LDCBF_HD void qp_trip(const StepConst& C, double* ws, QpState<N, MO>& s) {
         int bid = i_leg;
         if (b_vel < best) { best = b_vel; bid = i_vel; }
         if (b_cbf < best) { best = b_cbf; bid = i_cbf; }
-        const bool force_leg = s.pref == 0 && b_leg < -C.eps_active, force_vel = s.pref == 1 && b_vel < -C.eps_active;
+        const bool force_leg = s.pref == 0 && b_leg < -s.tol, force_vel = s.pref == 1 && b_vel < -s.tol;
         // obstacles beyond the register-resident MO: one streaming pass over (c, eta) in global memory (L1/L2)
         for (int o = 0; o < s.ns; ++o) {
             const double4 c4 = s.ces[o];
@@ -416,7 +418,7 @@ LDCBF_HD void qp_trip(const StepConst& C, double* ws, QpState<N, MO>& s) {
                 if (v < best) { best = v; bid = 4 * N + N * MO + (k - 1) * s.ns + o; }
             }
         }
-        if (!(best < -C.eps_active)) { s.done = true; return; }   // primal feasible: optimal
+        if (!(best < -s.tol)) { s.done = true; return; }   // primal feasible: optimal
         if (force_leg) { best = b_leg; bid = i_leg; }
         if (force_vel) { best = b_vel; bid = i_vel; }
         const double bsg = (bid < 4 * N && ((upper >> bid) & 1u)) ? -1.0 : 1.0;
@@ -503,7 +505,30 @@ LDCBF_HD void qp_trip(const StepConst& C, double* ws, QpState<N, MO>& s) {
     const int ldrop = tj[0];
     // full step t2 = -s_p / zz
     const bool full = !dependent && (ldrop < 0 || (-s.s_p) * t1d <= t1n * zz);
-    if (!full && ldrop < 0) { s.status = LDCBF_STATUS_INFEASIBLE; s.done = true; return; }
+    if (!full && ldrop < 0) {
+        // Row p cannot be satisfied together with the active rows.  When it is only violated by rounding-level amounts
+        // (<= eps_infeasible, 1e-9 m or m/s: kinematic rows that meet as equalities leave a feasible set that is a
+        // single point to rounding — IPOPT with constr_viol_tol 1e-5 and the NNLS oracle both return that point) the
+        // solve is restarted ONCE from the empty active set with rows counted as violated only below -eps_infeasible;
+        // otherwise the QP is infeasible (the reference's IPOPT raises, HumanoidMpc.py:419-429).
+        if (s.tol < C.eps_infeasible && -s.s_p <= C.eps_infeasible) {
+            s.tol = C.eps_infeasible;
+#pragma unroll
+            for (int k = 1; k <= N; ++k) { s.px[k] = s.gx; s.py[k] = s.gy; }
+            s.amask = 0;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                s.u[j] = 0.0; s.np[j] = 0.0;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) { AN(j, i) = 0.0; GM(j, i) = (i == j) ? 1.0 : 0.0; }
+                RC(j) = -1.0;
+            }
+            s.nn = 1.0; s.s_p = 0.0; s.u_p = 0.0; s.p_code = 0;
+            s.need_scan = true;
+            return;
+        }
+        s.status = LDCBF_STATUS_INFEASIBLE; s.done = true; return;
+    }
     // one division, not two (a 123-cycle chain on B200).  A reciprocal seed + two Newton steps (60 cycles, 1-2 ulp)
     // was tried: 2 % faster, but a full step then no longer lands its row on the bound to the last bit, and the
     // closed loop of config 1 with delta = 0 ended on an obstacle edge (status 3) at step 31 instead of at the goal.

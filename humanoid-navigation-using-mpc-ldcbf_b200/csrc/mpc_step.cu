@@ -443,7 +443,7 @@ extern "C" void ldcbf_params_default(ldcbf_params* p) {
     p->omega_max = 0.156 * 3.141592653589793; p->omega_min = -p->omega_max;        // HumanoidMpc.py:21-22
     p->foot_offset = 0.05; p->stop_objective = 0.05;                               // HumanoidMpc.py:200,392
     p->sampling_time = 1e-3;                                                       // HumanoidMpc.py:50
-    p->eps_active = 1e-12; p->eps_const_row = 1e-6;
+    p->eps_active = 1e-12; p->eps_const_row = 1e-6; p->eps_infeasible = 1e-9;
     p->max_iter = 200; p->flags = 0;
 }
 

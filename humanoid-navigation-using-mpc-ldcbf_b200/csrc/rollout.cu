@@ -12,6 +12,8 @@
 // Mapping: one thread per scenario, persistent over all its steps: no per-step launch latency, the
 // scenario's vertex rings stay in L1/L2 (832 B at the basic shape), state and active data in registers.
 // Scenarios are independent, so a block never synchronises.
+#include <cstdlib>
+
 #include "halfplane_dev.cuh"
 #include "mpc_qp.cuh"
 
@@ -199,6 +201,9 @@ static int launch_rollout(const StepConst& C, int B, int T, int n_goals, int msg
     // 1 lane 5.42 / 6.28 ms, 4 lanes 5.01 / 5.45 ms, 8 lanes 7.35 / 6.00 ms (eight times the warps of this large kernel
     // at different places in its code: the time then goes to instruction fetch).
     if (B < 148 * 4 * 16 && max_verts > 8) {
+        static const int rb = getenv("LDCBF_ROLLOUT_BLOCK") ? atoi(getenv("LDCBF_ROLLOUT_BLOCK")) : 32;
+        if (!io.fast_geometry && rb == 8) return launch_rollout_block<N, MO, true, 8, 4>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
+        if (!io.fast_geometry && rb == 16) return launch_rollout_block<N, MO, true, 16, 4>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
         return io.fast_geometry ? launch_rollout_block<N, MO, false, 32, 4>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st)
                                 : launch_rollout_block<N, MO, true, 32, 4>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
     }

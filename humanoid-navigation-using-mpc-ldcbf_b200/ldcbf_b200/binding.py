@@ -27,7 +27,8 @@ class LdcbfParams(ctypes.Structure):
                 ("l_max_x", c_double), ("l_max_y", c_double), ("l_min_x", c_double), ("l_min_y", c_double),
                 ("v_min", c_double * 2), ("v_max", c_double * 2), ("omega_max", c_double), ("omega_min", c_double),
                 ("foot_offset", c_double), ("stop_objective", c_double), ("sampling_time", c_double),
-                ("eps_active", c_double), ("eps_const_row", c_double), ("max_iter", c_int32), ("flags", c_int32)]
+                ("eps_active", c_double), ("eps_const_row", c_double), ("max_iter", c_int32), ("flags", c_int32),
+                ("eps_infeasible", c_double)]
 
 
 FLAG_FAST_GEOMETRY = 1

@@ -77,6 +77,9 @@ typedef struct ldcbf_params {
     double eps_const_row;   /* tolerance on the constant k = 0 LDCBF rows (1e-6, BASELINE.json) */
     int32_t max_iter;       /* active-set iteration cap per solve */
     int32_t flags;          /* LDCBF_FLAG_* */
+    double eps_infeasible;  /* a QP is reported infeasible only when the row that cannot be satisfied is violated by more
+                               than this (1e-9, natural units): below it the feasible set is a point to rounding and the
+                               solve is repeated with rows counted as violated only below -eps_infeasible (ABI 2) */
 } ldcbf_params;
 
 /* flags.  Default 0: the half-plane builder restates the reference's arithmetic bit for bit.

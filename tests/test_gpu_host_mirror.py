@@ -145,7 +145,8 @@ def test_subgoal_sequencing_matches_oracle():
         # a run ends because its stop rule fired (then it is near its sub-goal) or because the next QP is
         # infeasible (the reference breaks, HumanoidMpc.py:419-429, and the next sub-goal run starts from there)
         assert end in (0, 2)
-        if end == 0:
+        exhausted = Ug.shape[1] == 120 - 1      # all num_inputs steps used (pressed against the wall): :458 drops a column
+        if end == 0 and not exhausted:
             assert ((Xg[[0, 2], -1] - np.array(sg)) ** 2).sum() < 0.2
         s0 = e + 1
 
