@@ -46,7 +46,8 @@ constexpr int CL_MAXC = 64;
 //   unsigned coremask[RP/32]
 //   int ray[RP], lab[RP], cid[RP]  ray index; component label (smallest core index), later the cluster number; cluster
 //                                  number of a root
-//   int hn[64], slot[64]           hull size and output slot per cluster (at most 64 clusters are hulled)
+//   int hn[64], slot[64], cstart[64], cn[64]   hull size, output slot, member-list start and length per cluster (at most
+//                                  64 clusters are hulled)
 struct ClusterLayout {
     int RP, W;
     size_t off_y, off_region, off_core, off_ray, off_lab, off_cid, off_hn, bytes;
@@ -65,7 +66,7 @@ struct ClusterLayout {
         o += sizeof(int) * RP; off_lab = o;
         o += sizeof(int) * RP; off_cid = o;
         o += sizeof(int) * RP; off_hn = o;
-        o += sizeof(int) * CL_MAXC * 2;
+        o += sizeof(int) * CL_MAXC * 4;
         bytes = (o + 15) & ~(size_t)15;
     }
 };
@@ -100,6 +101,8 @@ __global__ void __launch_bounds__(CL_THREADS) lidar_clusters_kernel(int R, const
     int* CID = reinterpret_cast<int*>(cl_raw + Lo.off_cid);
     int* HN = reinterpret_cast<int*>(cl_raw + Lo.off_hn);
     int* SLOT = HN + CL_MAXC;
+    int* CSTART = SLOT + CL_MAXC;
+    int* CN = CSTART + CL_MAXC;
     __shared__ int sP, sNC, sChanged, sOut, sOvf;
 
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31;
@@ -235,36 +238,37 @@ __global__ void __launch_bounds__(CL_THREADS) lidar_clusters_kernel(int R, const
         labels[(size_t)b * R + RAY[i]] = (c == CL_BIG) ? -1 : c;
         LAB[i] = c;
     }
-    if (t < CL_MAXC) { HN[t] = 0; SLOT[t] = -1; }
+    if (t < CL_MAXC) { HN[t] = 0; SLOT[t] = -1; CN[t] = 0; CSTART[t] = 0; }
     __syncthreads();                      // the eps-graph has been read for the last time: its memory becomes MEM / FLG / POS
     for (int i = t; i < P; i += CL_THREADS) POS[i] = -1;
     __syncthreads();
 
-    // ---- 6. hulls: one warp per cluster
+    // ---- 6. hulls.  (a) one warp per cluster: member list (ray order), lexicographic extremes, flatness rule
     {
         const int warp = t >> 5;
         int* mem = MEM + warp * Lo.RP;
         const unsigned lt = (1u << lane) - 1u;
+        int used = 0;                                                      // this warp's lists sit back to back in `mem`
         for (int c = warp; c < nc; c += CL_WARPS) {
             int n = 0;
-            for (int base = 0; base < P; base += 32) {                     // members of cluster c, in ray order
+            for (int base = 0; base < P; base += 32) {
                 const int i = base + lane;
                 const bool ok = i < P && LAB[i] == c;
                 const unsigned m = __ballot_sync(0xffffffffu, ok);
-                if (ok) mem[n + __popc(m & lt)] = i;
+                if (ok) mem[used + n + __popc(m & lt)] = i;
                 n += __popc(m);
             }
             __syncwarp();
-            int h = 0;
+            bool keep = false;
             if (n >= 3) {
-                // lexicographic extremes, then the reference's flatness rule: it drops a cluster when
-                // np.linalg.matrix_rank(points - points[0]) < 2 (`:75-76`) or when Qhull finds the input flat to its
-                // roundoff bound and raises (`:81-83`; ~23 eps max|coordinate|).  Both only ever trigger on readings
-                // taken on ONE straight edge (deviations ~1e-16); real corners deviate by >= 1e-6.  One test covers both:
-                // largest distance from the line through the lexicographic extremes <= 64 eps max|coordinate|.
+                // The reference drops a cluster when np.linalg.matrix_rank(points - points[0]) < 2 (`:75-76`) or when
+                // Qhull finds the input flat to its roundoff bound and raises (`:81-83`; ~23 eps max|coordinate|).  Both
+                // only ever trigger on readings taken on ONE straight edge (deviations ~1e-16); real corners deviate by
+                // >= 1e-6.  One test covers both: largest distance from the line through the lexicographic extremes
+                // <= 64 eps max|coordinate|.
                 double lox = INFINITY, loy = INFINITY, hix = -INFINITY, hiy = -INFINITY, scale = 0.0;
                 for (int k = lane; k < n; k += 32) {
-                    const double px = X[mem[k]], py = Y[mem[k]];
+                    const double px = X[mem[used + k]], py = Y[mem[used + k]];
                     if (lex_less(px, py, lox, loy)) { lox = px; loy = py; }
                     if (lex_less(hix, hiy, px, py)) { hix = px; hiy = py; }
                     scale = fmax(scale, fmax(fabs(px), fabs(py)));
@@ -280,72 +284,75 @@ __global__ void __launch_bounds__(CL_THREADS) lidar_clusters_kernel(int R, const
                 const double dxl = hix - lox, dyl = hiy - loy;
                 double maxcross = 0.0;
                 for (int k = lane; k < n; k += 32)
-                    maxcross = fmax(maxcross, fabs(cross2(dxl, dyl, X[mem[k]] - lox, Y[mem[k]] - loy)));
+                    maxcross = fmax(maxcross, fabs(cross2(dxl, dyl, X[mem[used + k]] - lox, Y[mem[used + k]] - loy)));
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) maxcross = fmax(maxcross, __shfl_xor_sync(0xffffffffu, maxcross, off));
                 const double maxdev = maxcross / sqrt(dxl * dxl + dyl * dyl);      // NaN when all points coincide
-                if (maxdev > 64.0 * 2.220446049250313e-16 * scale) {
-                    // classification: lane k takes points k, k + 32, ...; every partner is a shared-memory broadcast
-                    for (int k = lane; k < n; k += 32) {
-                        const int i = mem[k];
-                        const double xi = X[i], yi = Y[i];
-                        bool haveL = false, haveR = false, dup = false;
-                        double dnx = 0.0, dny = 0.0, dxx = 0.0, dxy = 0.0;         // min / max angle of p_i - a, a < p_i
-                        double enx = 0.0, eny = 0.0, exx = 0.0, exy = 0.0;         // min / max angle of b - p_i, b > p_i
-                        for (int a = 0; a < n; ++a) {
-                            const int j = mem[a];
-                            const double xa = X[j], ya = Y[j];
-                            if (xa == xi && ya == yi) { dup = dup || a < k; continue; }   // np.unique: first copy stays
-                            if (lex_less(xa, ya, xi, yi)) {
-                                const double dx = xi - xa, dy = yi - ya;
-                                if (!haveL) { dnx = dxx = dx; dny = dxy = dy; haveL = true; }
-                                else {
-                                    if (cross2(dx, dy, dnx, dny) > 0.0) { dnx = dx; dny = dy; }
-                                    if (cross2(dxx, dxy, dx, dy) > 0.0) { dxx = dx; dxy = dy; }
-                                }
-                            } else {
-                                const double ex = xa - xi, ey = ya - yi;
-                                if (!haveR) { enx = exx = ex; eny = exy = ey; haveR = true; }
-                                else {
-                                    if (cross2(ex, ey, enx, eny) > 0.0) { enx = ex; eny = ey; }
-                                    if (cross2(exx, exy, ex, ey) > 0.0) { exx = ex; exy = ey; }
-                                }
-                            }
-                        }
-                        const bool ext = !haveL || !haveR;
-                        const bool lo = !dup && (ext || cross2(dxx, dxy, enx, eny) > 0.0);
-                        const bool up = !dup && !lo && cross2(dnx, dny, exx, exy) < 0.0;
-                        FLG[i] = (lo ? 1 : 0) | (up ? 2 : 0);
+                keep = maxdev > 64.0 * 2.220446049250313e-16 * scale;
+            }
+            if (lane == 0) { CSTART[c] = warp * Lo.RP + used; CN[c] = keep ? n : 0; }
+            used += n;
+        }
+    }
+    __syncthreads();
+    // (b) one THREAD per point, all clusters at once: classify against the members of the point's own cluster (every
+    // partner coordinate is read through the member list; neighbouring threads mostly share the cluster)
+    for (int i = t; i < P; i += CL_THREADS) {
+        const int c = LAB[i];
+        int f = 0;
+        if (c < nc && CN[c] > 0) {
+            const int n = CN[c];
+            const int* mem = MEM + CSTART[c];
+            const double xi = X[i], yi = Y[i];
+            bool haveL = false, haveR = false, dup = false;
+            double dnx = 0.0, dny = 0.0, dxx = 0.0, dxy = 0.0;             // min / max angle of p_i - a, a < p_i
+            double enx = 0.0, eny = 0.0, exx = 0.0, exy = 0.0;             // min / max angle of b - p_i, b > p_i
+            for (int a = 0; a < n; ++a) {
+                const int j = mem[a];
+                const double xa = X[j], ya = Y[j];
+                if (xa == xi && ya == yi) { dup = dup || j < i; continue; }       // np.unique: the first copy stays
+                if (lex_less(xa, ya, xi, yi)) {
+                    const double dx = xi - xa, dy = yi - ya;
+                    if (!haveL) { dnx = dxx = dx; dny = dxy = dy; haveL = true; }
+                    else {
+                        if (cross2(dx, dy, dnx, dny) > 0.0) { dnx = dx; dny = dy; }
+                        if (cross2(dxx, dxy, dx, dy) > 0.0) { dxx = dx; dxy = dy; }
                     }
-                    __syncwarp();
-                    int n_lo = 0, n_up = 0;
-                    for (int base = 0; base < n; base += 32) {
-                        const int f = (base + lane < n) ? FLG[mem[base + lane]] : 0;
-                        n_lo += __popc(__ballot_sync(0xffffffffu, f & 1));
-                        n_up += __popc(__ballot_sync(0xffffffffu, f & 2));
-                    }
-                    h = n_lo + n_up;
-                    if (h >= 3) {
-                        for (int k = lane; k < n; k += 32) {
-                            const int i = mem[k], f = FLG[i];
-                            if (!f) continue;
-                            const double xi = X[i], yi = Y[i];
-                            int before = 0;
-                            for (int a = 0; a < n; ++a) {
-                                const int j = mem[a];
-                                if (FLG[j] != f) continue;
-                                // lower chain ascending, upper chain descending
-                                before += (f & 1) ? lex_less(X[j], Y[j], xi, yi) : lex_less(xi, yi, X[j], Y[j]);
-                            }
-                            POS[i] = (f & 1) ? before : n_lo + before;
-                        }
-                    } else {
-                        h = 0;
+                } else {
+                    const double ex = xa - xi, ey = ya - yi;
+                    if (!haveR) { enx = exx = ex; eny = exy = ey; haveR = true; }
+                    else {
+                        if (cross2(ex, ey, enx, eny) > 0.0) { enx = ex; eny = ey; }
+                        if (cross2(exx, exy, ex, ey) > 0.0) { exx = ex; exy = ey; }
                     }
                 }
             }
-            if (lane == 0) HN[c] = h;
-            __syncwarp();
+            const bool ext = !haveL || !haveR;
+            const bool lo = !dup && (ext || cross2(dxx, dxy, enx, eny) > 0.0);
+            const bool up = !dup && !lo && cross2(dnx, dny, exx, exy) < 0.0;
+            f = (lo ? 1 : 0) | (up ? 2 : 0);
+        }
+        FLG[i] = f;
+    }
+    __syncthreads();
+    // (c) vertex order: counter-clockwise from the lexicographic minimum = lower chain ascending, then upper chain
+    // descending; every vertex counts the vertices of its chain that come before it
+    for (int i = t; i < P; i += CL_THREADS) {
+        const int f = FLG[i];
+        if (!f) continue;
+        const int c = LAB[i], n = CN[c];
+        const int* mem = MEM + CSTART[c];
+        const double xi = X[i], yi = Y[i];
+        int before = 0, n_lo = 0, n_up = 0;
+        for (int a = 0; a < n; ++a) {
+            const int j = mem[a], fj = FLG[j];
+            n_lo += fj & 1;
+            n_up += (fj >> 1) & 1;
+            if (fj == f) before += (f & 1) ? lex_less(X[j], Y[j], xi, yi) : lex_less(xi, yi, X[j], Y[j]);
+        }
+        if (n_lo + n_up >= 3) {
+            POS[i] = (f & 1) ? before : n_lo + before;
+            if ((f & 1) && before == 0) HN[c] = n_lo + n_up;               // the lexicographic minimum reports the size
         }
     }
     __syncthreads();

@@ -204,7 +204,8 @@ struct QpState {
 template <int N>
 struct QpRecord {       // layout of a record, in doubles
     static constexpr int TH = 0, OM = TH + N + 1, RC_ = OM + N, RS_ = RC_ + N + 1, W = RS_ + N + 1, U = W + 2 * N,
-                         PACKED = U + 2 * N, WS0 = PACKED + 1, DOUBLES = WS0 + QpWorkspace<N>::DOUBLES;
+                         NP = U + 2 * N, NN = NP + 2 * N, SP = NN + 1, UP = SP + 1, PACKED = UP + 1, WS0 = PACKED + 1,
+                         DOUBLES = WS0 + QpWorkspace<N>::DOUBLES;
 };
 
 template <int N, int MO, int WS, bool RESUME = false>
@@ -299,9 +300,16 @@ LDCBF_HD void qp_setup(const StepConst& C, double p0x, double v0x, double p0y, d
         }
 #pragma unroll
         for (int j = 0; j < NV; ++j) s.u[j] = rec[(R::U + j) * stride];
-        const long long packed = (long long)rec[R::PACKED * stride];       // amask | iters << 8 (exact in a double)
+        // amask | need_scan << 8 | relaxed << 9 | p_code << 10 | iters << 24 (exact in a double)
+        const long long packed = (long long)rec[R::PACKED * stride];
         s.amask = (unsigned)(packed & 0xff);
-        s.iters = (int)(packed >> 8);
+        s.need_scan = ((packed >> 8) & 1) != 0;
+        if ((packed >> 9) & 1) s.tol = C.eps_infeasible;
+        s.p_code = (int)((packed >> 10) & 0x3fff);
+        s.iters = (int)(packed >> 24);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) s.np[j] = rec[(R::NP + j) * stride];
+        s.nn = rec[R::NN * stride]; s.s_p = rec[R::SP * stride]; s.u_p = rec[R::UP * stride];
 #pragma unroll
         for (int e = 0; e < QpWorkspace<N>::DOUBLES; ++e) ws[e * WS] = rec[(R::WS0 + e) * stride];
     }
@@ -309,7 +317,7 @@ LDCBF_HD void qp_setup(const StepConst& C, double p0x, double v0x, double p0y, d
 
 // The counterpart of qp_setup<RESUME>: what a scenario's solver state consists of after setup (+ warm start).
 template <int N, int MO, int WS>
-LDCBF_HD void qp_dump_state(const QpState<N, MO>& s, const double* ws, double* rec, size_t stride) {
+LDCBF_HD void qp_dump_state(const StepConst& C, const QpState<N, MO>& s, const double* ws, double* rec, size_t stride) {
     using R = QpRecord<N>;
     constexpr int NV = 2 * N;
 #pragma unroll
@@ -324,7 +332,12 @@ LDCBF_HD void qp_dump_state(const QpState<N, MO>& s, const double* ws, double* r
     }
 #pragma unroll
     for (int j = 0; j < NV; ++j) rec[(R::U + j) * stride] = s.u[j];
-    rec[R::PACKED * stride] = (double)((long long)s.amask | ((long long)s.iters << 8));
+#pragma unroll
+    for (int j = 0; j < NV; ++j) rec[(R::NP + j) * stride] = s.np[j];
+    rec[R::NN * stride] = s.nn; rec[R::SP * stride] = s.s_p; rec[R::UP * stride] = s.u_p;
+    rec[R::PACKED * stride] = (double)((long long)s.amask | ((long long)(s.need_scan ? 1 : 0) << 8) |
+                                       ((long long)(s.tol > C.eps_active ? 1 : 0) << 9) | ((long long)(s.p_code & 0x3fff) << 10) |
+                                       ((long long)s.iters << 24));
 #pragma unroll
     for (int e = 0; e < QpWorkspace<N>::DOUBLES; ++e) rec[(R::WS0 + e) * stride] = ws[e * WS];
 }
@@ -613,12 +626,15 @@ LDCBF_HD void qp_warm_start(const StepConst& C, const int (&codes)[2 * N], doubl
             for (int o = 0; o < MO; ++o) cbf[k * MO + o] = s.ex[o] * s.px[kk] + s.ey[o] * s.py[kk] - s.hb[o];
         }
     }
-    double rhs[NV];
+    // One copy of the row decoding in the instruction stream (the loop is not unrolled: the kernels that call this every
+    // step are bound by instruction fetch); slot j is addressed dynamically in the workspace, its right-hand side is
+    // parked in the first row of the Gram block, which is only built in the rounds below.
     unsigned mask = 0;
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < NV; ++j) {
-        rhs[j] = 0.0;
-        const int code = codes[j];
+        int code = -1;
+#pragma unroll
+        for (int jj = 0; jj < NV; ++jj) if (jj == j) code = codes[jj];
         const int id = code >> 1;
         bool ok = code >= 0 && id < 4 * N + N * MO;
         double sl = 0.0;
@@ -636,16 +652,20 @@ LDCBF_HD void qp_warm_start(const StepConst& C, const int (&codes)[2 * N], doubl
                 for (int i = 0; i < N * MO; ++i) if (i == q) sl = cbf[i];
             }
         }
+        GM(0, j) = 0.0;
         if (ok) {
             double a[NV];
             row_normal<N, MO>(id, sg, C.gtil, s.rc, s.rs, s.ft, s.ex, s.ey, s.ces, s.ns, a);
 #pragma unroll
             for (int i = 0; i < NV; ++i) AN(j, i) = a[i];
             RC(j) = (double)code;
-            rhs[j] = -sl;
+            GM(0, j) = -sl;
             mask |= 1u << j;
         }
     }
+    double rhs[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) rhs[j] = GM(0, j);
     if (mask == 0u) return;
     bool fail = false;
     double uu[NV];

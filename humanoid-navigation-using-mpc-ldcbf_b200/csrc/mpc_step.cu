@@ -104,13 +104,17 @@ __global__ void __launch_bounds__(BLOCK) mpc_qp_kernel(StepConst C, int B, int m
 // lanes) instead of ~2500 instructions of setup and warm start inside this divergent region.
 template <int N, int MO, int BLOCK, int TRIPS, bool RESUME, int MIN_IDLE>
 __global__ void __launch_bounds__(BLOCK) mpc_qp_refill_kernel(StepConst C, int b0, int Bc, int max_obs, int per_warp,
-                                                            StepIO io, const double* __restrict__ rec) {
+                                                            StepIO io, const double* __restrict__ rec,
+                                                            const int* __restrict__ ids, const int* __restrict__ count) {
     extern __shared__ double qp_ws[];
     double* ws = qp_ws + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     const int warp = (blockIdx.x * BLOCK + threadIdx.x) >> 5;
-    const int B = b0 + Bc;
-    long long first = (long long)b0 + (long long)warp * per_warp;
+    // RESUME: the work list is the compacted set of scenarios the prepare kernel left unfinished — record k belongs to
+    // scenario ids[k], k < *count; the chunk cursor then runs over k.  Otherwise it runs over the scenarios themselves.
+    if (RESUME) per_warp = (*count + (int)(gridDim.x * (BLOCK / 32)) - 1) / (int)(gridDim.x * (BLOCK / 32));
+    const int B = RESUME ? *count : b0 + Bc;
+    long long first = (RESUME ? 0LL : (long long)b0) + (long long)warp * per_warp;
     int next = first < B ? (int)first : B;                       // warp-uniform chunk cursor
     const int end = min(B, next + per_warp);
     QpState<N, MO> s;
@@ -134,7 +138,7 @@ __global__ void __launch_bounds__(BLOCK) mpc_qp_refill_kernel(StepConst C, int b
                 const unsigned free_m = __ballot_sync(0xffffffffu, b < 0);
                 const int cand = next + __popc(free_m & ((1u << lane) - 1u));
                 if (b < 0 && cand < end) {
-                    b = cand;
+                    b = RESUME ? ids[cand] : cand;
                     double4 x;
                     double th0;
                     load_state(io, b, x, th0);
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(BLOCK) mpc_qp_refill_kernel(StepConst C, int b
                     for (int o = 0; o < MO; ++o) ce[o] = (o < nb) ? gce[o] : make_double4(0.0, 0.0, 0.0, 0.0);
                     qp_setup<N, MO, BLOCK, RESUME>(C, x.x, x.y, x.z, x.w, th0, g.x, g.y, ft, ce, nb, gce + MO, nt - nb,
                                                    io.delta ? io.delta[b] : 0.0, lim, ws, s,
-                                                   RESUME ? rec + (b - b0) : nullptr, (size_t)Bc);
+                                                   RESUME ? rec + cand : nullptr, (size_t)Bc);
                 }
                 next = min(end, next + __popc(free_m));
             }
@@ -164,36 +168,64 @@ __global__ void __launch_bounds__(BLOCK) mpc_qp_refill_kernel(StepConst C, int b
 }
 
 // Large batches, first half: one thread per scenario runs the fixed part of a solve — heading schedule (atan2, N+1
-// sincos), bounds, geometric guess, warm start (Gram matrix, Cholesky, sign repair) — with every lane of every warp
-// busy, and writes the resulting solver state as a record, element-major over the chunk (coalesced).
-template <int N, int MO, int BLOCK>
+// sincos), bounds, geometric guess, warm start (Gram matrix, Cholesky, sign repair) — and the first K0 trips, every
+// warp starting with all lanes busy.  Half of the scenarios are finished by then (p50 of the trip count is 3) and
+// store their result here; the others append their solver state as a record to a COMPACT list (warp-aggregated
+// atomic; element-major over the list positions, so both sides stay coalesced) which the resume kernel works through
+// with lane refill.  Which position a scenario gets depends on the order the warps arrive in, its result does not.
+template <int N, int MO, int BLOCK, int K0>
 __global__ void __launch_bounds__(BLOCK) mpc_qp_prepare_kernel(StepConst C, int b0, int Bc, int max_obs, StepIO io,
-                                                             double* __restrict__ rec) {
+                                                             double* __restrict__ rec, int* __restrict__ ids,
+                                                             int* __restrict__ count) {
     extern __shared__ double qp_ws[];
     const int i = blockIdx.x * BLOCK + threadIdx.x;
-    if (i >= Bc) return;
-    const int b = b0 + i;
-    double4 x;
-    double th0;
-    load_state(io, b, x, th0);
-    const double2 g = reinterpret_cast<const double2*>(io.goal)[b];
-    int ft[N + 1];
-    load_foot<N>(io, b, ft);
-    const Limits lim = load_limits(C, io.limits, (size_t)b);
-    const int nt = min(io.nobs[b], max_obs);
-    const int nb = min(nt, MO);
-    double4 ce[MO];
-    const double4* gce = reinterpret_cast<const double4*>(io.c_eta) + (size_t)b * max_obs;
-#pragma unroll
-    for (int o = 0; o < MO; ++o) ce[o] = (o < nb) ? gce[o] : make_double4(0.0, 0.0, 0.0, 0.0);
+    const bool live = i < Bc;
+    const int b = b0 + (live ? i : 0);
     double* ws = qp_ws + threadIdx.x;
     QpState<N, MO> s;
-    qp_setup<N, MO, BLOCK>(C, x.x, x.y, x.z, x.w, th0, g.x, g.y, ft, ce, nb, gce + MO, nt - nb,
-                           io.delta ? io.delta[b] : 0.0, lim, ws, s);
-    int codes[2 * N];
-    guess_codes<N, MO>(s, codes);
-    qp_warm_start<N, MO, BLOCK>(C, codes, ws, s);
-    qp_dump_state<N, MO, BLOCK>(s, ws, rec + i, (size_t)Bc);
+    s.done = true;
+    if (live) {
+        double4 x;
+        double th0;
+        load_state(io, b, x, th0);
+        const double2 g = reinterpret_cast<const double2*>(io.goal)[b];
+        int ft[N + 1];
+        load_foot<N>(io, b, ft);
+        const Limits lim = load_limits(C, io.limits, (size_t)b);
+        const int nt = min(io.nobs[b], max_obs);
+        const int nb = min(nt, MO);
+        double4 ce[MO];
+        const double4* gce = reinterpret_cast<const double4*>(io.c_eta) + (size_t)b * max_obs;
+#pragma unroll
+        for (int o = 0; o < MO; ++o) ce[o] = (o < nb) ? gce[o] : make_double4(0.0, 0.0, 0.0, 0.0);
+        qp_setup<N, MO, BLOCK>(C, x.x, x.y, x.z, x.w, th0, g.x, g.y, ft, ce, nb, gce + MO, nt - nb,
+                               io.delta ? io.delta[b] : 0.0, lim, ws, s);
+        int codes[2 * N];
+        guess_codes<N, MO>(s, codes);
+        qp_warm_start<N, MO, BLOCK>(C, codes, ws, s);
+#pragma unroll 1
+        for (int t = 0; t < K0; ++t) {
+            if (!s.done) qp_trip<N, MO, BLOCK>(C, ws, s);
+        }
+        if (s.done) {
+            QpSolution<N> S;
+            qp_finish<N, MO>(C, s, S);
+            store_solution<N>(S, b, io);
+        }
+    }
+    const bool open = live && !s.done;
+    const unsigned m = __ballot_sync(0xffffffffu, open);
+    if (m) {
+        const unsigned lane = threadIdx.x & 31u;
+        int base = 0;
+        if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(count, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (open) {
+            const int k = base + __popc(m & ((1u << lane) - 1u));
+            ids[k] = b;
+            qp_dump_state<N, MO, BLOCK>(C, s, ws, rec + k, (size_t)Bc);
+        }
+    }
 }
 
 // Batches that do not fill the GPU: G lanes per scenario (mpc_qp_coop.cuh).  BLOCK / G scenarios per block, each with
@@ -367,19 +399,27 @@ static int launch_qp(const StepConst& C, int B, int max_obs, const StepIO& io, c
             auto kern = mpc_qp_refill_kernel<N, MO, BLOCK, TRIPS, false, LDCBF_QP_REFILL_MIN_IDLE>;
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) { set_last_error(e); return LDCBF_E_LAUNCH; }
-            kern<<<148 * 2, BLOCK, smem, st>>>(C, 0, B, max_obs, (B + warps - 1) / warps, io, nullptr);
+            kern<<<148 * 2, BLOCK, smem, st>>>(C, 0, B, max_obs, (B + warps - 1) / warps, io, nullptr, nullptr, nullptr);
             return check_launch();
         }
-        // prepare (convergent) + resume (lane refill from records), in chunks of at most 2^20 scenarios so that the
-        // stream-ordered record buffer stays below 1 GB; HBM is otherwise idle in these FP64-bound kernels
+        // prepare (convergent: fixed part + first trips) + resume (lane refill from the records of the unfinished), in
+        // chunks of at most 2^20 scenarios so that the stream-ordered record buffer stays below 1 GB
         constexpr int CHUNK = 1 << 20;
         const int Bmax = B < CHUNK ? B : CHUNK;
-        double* rec = nullptr;
+        char* buf = nullptr;
         cudaMemPool_t pool = workspace_pool();
-        cudaError_t e = pool ? cudaMallocFromPoolAsync(&rec, (size_t)QpRecord<N>::DOUBLES * sizeof(double) * Bmax, pool, st)
-                             : cudaErrorMemoryAllocation;
+        const size_t rec_bytes = (size_t)QpRecord<N>::DOUBLES * sizeof(double) * Bmax;
+        const size_t ids_bytes = ((size_t)Bmax * sizeof(int) + 15) / 16 * 16;
+        cudaError_t e = pool ? cudaMallocFromPoolAsync(&buf, rec_bytes + ids_bytes + 16, pool, st) : cudaErrorMemoryAllocation;
         if (e != cudaSuccess) { set_last_error(e); cudaGetLastError(); return LDCBF_E_LAUNCH; }
-        auto prep = mpc_qp_prepare_kernel<N, MO, BLOCK>;
+        double* rec = reinterpret_cast<double*>(buf);
+        int* ids = reinterpret_cast<int*>(buf + rec_bytes);
+        int* count = reinterpret_cast<int*>(buf + rec_bytes + ids_bytes);
+        static const int k0 = env_int("LDCBF_PREP_TRIPS", 2);
+        auto prep = k0 <= 0 ? mpc_qp_prepare_kernel<N, MO, BLOCK, 0>
+                  : k0 == 1 ? mpc_qp_prepare_kernel<N, MO, BLOCK, 1>
+                  : k0 == 2 ? mpc_qp_prepare_kernel<N, MO, BLOCK, 2>
+                  : k0 == 3 ? mpc_qp_prepare_kernel<N, MO, BLOCK, 3> : mpc_qp_prepare_kernel<N, MO, BLOCK, 4>;
         auto kern = mpc_qp_refill_kernel<N, MO, BLOCK, TRIPS, true, LDCBF_QP_RESUME_MIN_IDLE>;
         e = cudaFuncSetAttribute(prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -387,11 +427,12 @@ static int launch_qp(const StepConst& C, int B, int max_obs, const StepIO& io, c
         if (e != cudaSuccess) { set_last_error(e); rc = LDCBF_E_LAUNCH; }
         for (int b0 = 0; b0 < B && rc == LDCBF_OK; b0 += CHUNK) {
             const int Bc = (B - b0) < CHUNK ? (B - b0) : CHUNK;
-            prep<<<(unsigned)((Bc + BLOCK - 1) / BLOCK), BLOCK, smem, st>>>(C, b0, Bc, max_obs, io, rec);
-            kern<<<148 * 2, BLOCK, smem, st>>>(C, b0, Bc, max_obs, (Bc + warps - 1) / warps, io, rec);
+            cudaMemsetAsync(count, 0, sizeof(int), st);
+            prep<<<(unsigned)((Bc + BLOCK - 1) / BLOCK), BLOCK, smem, st>>>(C, b0, Bc, max_obs, io, rec, ids, count);
+            kern<<<148 * 2, BLOCK, smem, st>>>(C, b0, Bc, max_obs, 0, io, rec, ids, count);
             rc = check_launch();
         }
-        cudaFreeAsync(rec, st);
+        cudaFreeAsync(buf, st);
         return rc;
     }
     if (B >= 148 * 4 * 128) return launch_qp_block<N, MO, 128>(C, B, max_obs, io, st);

@@ -48,8 +48,8 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
     const bool right_first = io.right_first[b] != 0;
     const int nt = min(io.nobs[b], max_obs);
     const int nb = min(nt, MO);
-    double4* ces = io.ce_scratch ? io.ce_scratch + (size_t)b * max_obs : nullptr;   // obstacles MO.. are streamed
-    const int n_stream = ces ? nt - nb : 0;
+    double4* ces = io.ce_scratch + (size_t)b * max_obs;     // half-planes of this step; obstacles MO.. are streamed from here
+    const int n_stream = nt - nb;
     const double dl = io.delta ? io.delta[b] : 0.0;
     const Limits lim = load_limits(C, io.limits, (size_t)b);
     double* tX = (io.traj_X && writer) ? io.traj_X + (size_t)b * (T + 1) * 5 : nullptr;
@@ -87,25 +87,21 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
             io.state[5 * (size_t)b + 3] = vy; io.state[5 * (size_t)b + 4] = th;                  // store equal values)
         }
         if (kstep % substeps == 0) {
-            // half-planes at the current CoM (:387)
-            double4 ce[MO];
-#pragma unroll
-            for (int o = 0; o < MO; ++o) {
-                ce[o] = make_double4(0.0, 0.0, 0.0, 0.0);
-                if (o < nb) {
-                    const int V = min(io.nverts[(size_t)b * max_obs + o], max_verts);
-                    if (V > 0)
-                        ce[o] = halfplane_group<EXACT, G>(px, py, io.verts + ((size_t)b * max_obs + o) * max_verts, V,
-                                                          glane, gmask);
-                }
-            }
-            // every lane of the group stores the same value and later reads back its own store: no synchronisation
-            for (int o = MO; o < MO + n_stream; ++o) {
+            // half-planes at the current CoM (:387).  ONE copy of the ring walk in the instruction stream (the loop over
+            // obstacles is not unrolled: this kernel is bound by instruction fetch — ncu: 1.9 of 5.3 cycles per issued
+            // instruction wait for the next instruction, the loop body of a step is ~170 KB against a 32 KB L1.5
+            // instruction cache); the results go through the scratch row of the scenario, every lane of the group
+            // stores the same value and reads back its own store
+#pragma unroll 1
+            for (int o = 0; o < nt; ++o) {
                 const int V = min(io.nverts[(size_t)b * max_obs + o], max_verts);
                 ces[o] = V > 0 ? halfplane_group<EXACT, G>(px, py, io.verts + ((size_t)b * max_obs + o) * max_verts, V,
                                                            glane, gmask)
                                : make_double4(0.0, 0.0, 0.0, 0.0);
             }
+            double4 ce[MO];
+#pragma unroll
+            for (int o = 0; o < MO; ++o) ce[o] = (o < nb) ? ces[o] : make_double4(0.0, 0.0, 0.0, 0.0);
             int ft[N + 1];
             const int step_number = kstep / substeps;                                 // :401
 #pragma unroll
@@ -114,7 +110,7 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
             {
                 QpState<N, MO> qs;
                 double* ws = qp_ws + threadIdx.x;
-                qp_setup<N, MO, BLOCK>(C, px, vx, py, vy, th, gx, gy, ft, ce, nb, ces ? ces + MO : nullptr, n_stream, dl, lim, ws, qs);
+                qp_setup<N, MO, BLOCK>(C, px, vx, py, vy, th, gx, gy, ft, ce, nb, ces + MO, n_stream, dl, lim, ws, qs);
                 if (io.warm_start) {
                     bool any = false;                       // nothing carried over (first step of a run): geometric guess
 #pragma unroll
@@ -242,10 +238,11 @@ extern "C" int ldcbf_rollout_f64(const ldcbf_params* prm, int B, int N, int T, i
     int sub = (int)(prm->delta_t / prm->sampling_time);                      // HumanoidMpc.py:74-75
     if (sub <= 0) sub = 1;
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    // more obstacles than the register-resident 8 (the reference's CROWDED maps have 20, simulation_1.py:201-231):
-    // their half-planes go through a stream-ordered scratch from the library's pool, 32 B per (scenario, obstacle)
+    // the half-planes of a step go through a stream-ordered scratch from the library's pool, 32 B per (scenario,
+    // obstacle): up to 8 are then held in registers, further ones (the reference's CROWDED maps have 20,
+    // simulation_1.py:201-231) are streamed from it during the scans
     double4* scratch = nullptr;
-    if (max_obs > LDCBF_MAX_OBSTACLES) {
+    {
         cudaMemPool_t pool = workspace_pool();
         cudaError_t e = pool ? cudaMallocFromPoolAsync(&scratch, sizeof(double4) * (size_t)B * max_obs, pool, st)
                              : cudaErrorMemoryAllocation;
