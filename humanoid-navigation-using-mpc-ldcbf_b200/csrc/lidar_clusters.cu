@@ -9,72 +9,69 @@
 //                                                            dropped again by the ConvexHull call of
 //                                                            HumanoidMPCUnknownEnvironment.py:55, so it is not emitted)
 //
-// One 256-thread CTA per scan (R <= 512 rays).  DBSCAN on <= 512 points is done exactly as sklearn defines it:
+// One 256-thread CTA per scan (R <= 512 rays; measured 128 -> 256 threads: 1.83 -> 1.72 ms for 16384 scans).  DBSCAN on <= 512 points is done exactly as sklearn defines it:
 //   * neighbourhood = points within eps (squared distances, self included); core = at least min_samples neighbours;
 //   * clusters = connected components of core points, numbered by their smallest core-point index (sklearn visits
 //     points in index order and opens a cluster at the first unvisited core point);
 //   * a border point takes the lowest-numbered cluster among its core neighbours (it is labelled by the first
 //     cluster that reaches it and never relabelled); everything else is noise (-1).
-// The eps-graph is held as a bit matrix in shared memory (R x R/32 words); components: every core point first takes its
-// lowest-indexed core neighbour (one find-first-set per point), chases that pointer to a root, and min-label
-// propagation sweeps then only have to confirm the fixed point (or repair the rare component that the forest split).
-// Hulls: one WARP per cluster, no sort and no sequential chain.  A point p_i is a vertex of the lower hull iff every
-// lexicographically smaller point a and greater point b make a strict left turn a -> p_i -> b.  All directions
-// p_i - a (and b - p_i) lie in one half-plane, where the sign of a cross product orders them by angle, so it is enough
-// to test the extreme pair: the largest-angle direction from the left against the smallest-angle direction to the
-// right (upper hull: mirrored).  Each lane classifies its points with one pass over the cluster (n^2 / 32 cross
-// products per warp, all lanes busy) where the previous version ran Andrew's monotone chain in ONE thread after a
-// 36-barrier bitonic sort of the whole scan (ncu: 19 of 32 lanes, 38 % of the stall samples on the barrier behind
-// the chain).  Vertex order (counter-clockwise from the lexicographic minimum: lower chain ascending, upper chain
-// descending) comes from counting, per vertex, the chain vertices before it.  Same strictly convex polygon as the
-// chain and as Qhull up to which of several points collinear to 1e-16 is called a vertex.  Exact duplicates
-// (np.unique of the reference) are skipped by index.
+// The eps-graph is held as a bit matrix in shared memory (R x R/32 words), components by min-label propagation.
+// Hulls: ONE bitonic sort of all clustered points by (cluster, x, y) turns every cluster into a contiguous segment in
+// np.unique order; then one thread per cluster removes duplicates, tests flatness and runs Andrew's monotone chain
+// (counter-clockwise, strictly convex), all clusters concurrently.  Qhull and the chain may disagree on which of
+// several points that are collinear to 1e-16 is called a vertex; the polygons are the same to rounding.
 #include "ldcbf_common.cuh"
 
 namespace ldcbf {
 
 constexpr int CL_RMAX = 512;
 constexpr int CL_THREADS = 256;
-constexpr int CL_WARPS = CL_THREADS / 32;
 constexpr int CL_BIG = 0x3fffffff;
-constexpr int CL_MAXC = 64;
 
-// Shared-memory layout, sized by RP = R rounded up to 32:
+// Shared-memory layout, sized by RP = R rounded up to 32 (and the sort arrays to the next power of two NS):
 //   double x[RP], y[RP]            compacted valid points, ray order
-//   REGION (one buffer, three lives): raw readings sx[RP], sy[RP] (step 1)  ->  eps-graph adj[RP][RP/32] (steps 2-4)
-//                                     ->  member lists mem[CL_WARPS][RP], flags flg[RP], hull positions pos[RP] (hulls)
+//   double sx[NS], sy[NS]          all clustered points sorted by (cluster, x, y)
+//   int    sc[NS]                  cluster number of the sorted points (CL_BIG = noise / padding)
+//   unsigned adj[RP][RP/32]        eps-graph
 //   unsigned coremask[RP/32]
-//   int ray[RP], lab[RP], cid[RP]  ray index; component label (smallest core index), later the cluster number; cluster
-//                                  number of a root
-//   int hn[64], slot[64], cstart[64], cn[64]   hull size, output slot, member-list start and length per cluster (at most
-//                                  64 clusters are hulled)
+//   int ray[RP], lab[RP], cid[RP]  ray index; component label (smallest core index); cluster number of a root
+//   int hull[NS + 64]              hull stacks, one region per cluster
+//   int seg0[64], segn[64], hn[64] segment start / length / hull size per cluster (at most 64 clusters are hulled)
 struct ClusterLayout {
-    int RP, W;
-    size_t off_y, off_region, off_core, off_ray, off_lab, off_cid, off_hn, bytes;
+    int RP, W, NS;
+    size_t off_y, off_sx, off_sy, off_sc, off_adj, off_core, off_ray, off_lab, off_cid, off_hull, off_seg, bytes;
     __host__ __device__ explicit ClusterLayout(int R) {
         RP = (R + 31) & ~31;
         W = RP / 32;
+        NS = 32;
+        while (NS < RP) NS <<= 1;
+        // The sort buffers (sx, sy, sc) and the eps-graph share one region: sx / sy stage the raw readings in step 1,
+        // before the graph is built (step 2), and are not written again until the graph has been read for the last
+        // time (border points, step 4).  10 KB less per block at R = 360 -> one more resident block per SM.
         size_t o = 0;
         o += sizeof(double) * RP; off_y = o;
-        o += sizeof(double) * RP; off_region = o;
-        size_t region = sizeof(double) * RP * 2;
-        const size_t adj_bytes = sizeof(unsigned) * RP * W, hull_bytes = sizeof(int) * RP * (CL_WARPS + 2);
-        region = adj_bytes > region ? adj_bytes : region;
-        region = hull_bytes > region ? hull_bytes : region;
-        o += region; off_core = o;
+        o += sizeof(double) * RP; off_sx = o;
+        const size_t sort_bytes = sizeof(double) * NS * 2 + sizeof(int) * NS;
+        const size_t adj_bytes = sizeof(unsigned) * RP * W;
+        off_sy = off_sx + sizeof(double) * NS;
+        off_sc = off_sy + sizeof(double) * NS;
+        off_adj = off_sx;
+        o += sort_bytes > adj_bytes ? sort_bytes : adj_bytes; off_core = o;
         o += sizeof(unsigned) * W; off_ray = o;
         o += sizeof(int) * RP; off_lab = o;
         o += sizeof(int) * RP; off_cid = o;
-        o += sizeof(int) * RP; off_hn = o;
-        o += sizeof(int) * CL_MAXC * 4;
+        o += sizeof(int) * RP; off_hull = o;
+        o += sizeof(int) * (NS + 64); off_seg = o;
+        o += sizeof(int) * 64 * 3;
         bytes = (o + 15) & ~(size_t)15;
     }
 };
 
-__device__ __forceinline__ bool lex_less(double ax, double ay, double bx, double by) {
-    return ax < bx || (ax == bx && ay < by);
+constexpr int CL_MAXC = 64;
+
+__device__ __forceinline__ bool key_less(int ac, double ax, double ay, int bc, double bx, double by) {
+    return ac < bc || (ac == bc && (ax < bx || (ax == bx && ay < by)));
 }
-__device__ __forceinline__ double cross2(double ax, double ay, double bx, double by) { return ax * by - ay * bx; }
 
 __global__ void __launch_bounds__(CL_THREADS) lidar_clusters_kernel(int R, const double2* __restrict__ hit_xy,
                                                                     const double2* __restrict__ noise, double eps2,
@@ -89,21 +86,19 @@ __global__ void __launch_bounds__(CL_THREADS) lidar_clusters_kernel(int R, const
     const int W = Lo.W;
     double* X = reinterpret_cast<double*>(cl_raw);
     double* Y = reinterpret_cast<double*>(cl_raw + Lo.off_y);
-    double* SX = reinterpret_cast<double*>(cl_raw + Lo.off_region);
-    double* SY = SX + Lo.RP;
-    unsigned* ADJ = reinterpret_cast<unsigned*>(cl_raw + Lo.off_region);
-    int* MEM = reinterpret_cast<int*>(cl_raw + Lo.off_region);          // [CL_WARPS][RP]
-    int* FLG = MEM + CL_WARPS * Lo.RP;
-    int* POS = FLG + Lo.RP;
+    double* SX = reinterpret_cast<double*>(cl_raw + Lo.off_sx);
+    double* SY = reinterpret_cast<double*>(cl_raw + Lo.off_sy);
+    int* SC = reinterpret_cast<int*>(cl_raw + Lo.off_sc);
+    unsigned* ADJ = reinterpret_cast<unsigned*>(cl_raw + Lo.off_adj);
     unsigned* CORE = reinterpret_cast<unsigned*>(cl_raw + Lo.off_core);
     int* RAY = reinterpret_cast<int*>(cl_raw + Lo.off_ray);
     int* LAB = reinterpret_cast<int*>(cl_raw + Lo.off_lab);
     int* CID = reinterpret_cast<int*>(cl_raw + Lo.off_cid);
-    int* HN = reinterpret_cast<int*>(cl_raw + Lo.off_hn);
-    int* SLOT = HN + CL_MAXC;
-    int* CSTART = SLOT + CL_MAXC;
-    int* CN = CSTART + CL_MAXC;
-    __shared__ int sP, sNC, sChanged, sOut, sOvf;
+    int* HULL = reinterpret_cast<int*>(cl_raw + Lo.off_hull);
+    int* SEG0 = reinterpret_cast<int*>(cl_raw + Lo.off_seg);
+    int* SEGN = SEG0 + CL_MAXC;
+    int* HN = SEGN + CL_MAXC;
+    __shared__ int sP, sNC, sChanged;
 
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31;
     const double2* scan = hit_xy + (size_t)b * R;
@@ -231,168 +226,145 @@ __global__ void __launch_bounds__(CL_THREADS) lidar_clusters_kernel(int R, const
     }
     __syncthreads();
     const int n_clusters = sNC;
+    int ns = 32;                                   // sort size: next power of two >= P
+    while (ns < P) ns <<= 1;
+    // labels out; sort keys (cluster, x, y) for every point, noise and padding last
+    for (int i = t; i < ns; i += CL_THREADS) {
+        int c = CL_BIG;
+        double px = INFINITY, py = INFINITY;
+        if (i < P) {
+            if (LAB[i] != CL_BIG) c = CID[LAB[i]];
+            labels[(size_t)b * R + RAY[i]] = (c == CL_BIG) ? -1 : c;
+            px = X[i]; py = Y[i];
+        }
+        SC[i] = c; SX[i] = px; SY[i] = py;
+    }
+    if (t < CL_MAXC) { SEG0[t] = 0; SEGN[t] = 0; HN[t] = 0; }
+    __syncthreads();
+
+    // ---- 6. ONE bitonic sort by (cluster, x, y): every cluster becomes a contiguous, np.unique-ordered segment
+    for (int k = 2; k <= ns; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = t; i < ns; i += CL_THREADS) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const int ac = SC[i], bc = SC[l];
+                    const double ax = SX[i], ay = SY[i], bx = SX[l], by = SY[l];
+                    if (key_less(bc, bx, by, ac, ax, ay) == up) {
+                        SC[i] = bc; SX[i] = bx; SY[i] = by; SC[l] = ac; SX[l] = ax; SY[l] = ay;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // segment boundaries
+    for (int i = t; i < ns; i += CL_THREADS) {
+        const int c = SC[i];
+        if (c < CL_MAXC) {
+            if (i == 0 || SC[i - 1] != c) SEG0[c] = i;
+            if (i == ns - 1 || SC[i + 1] != c) SEGN[c] = i + 1;        // end (exclusive)
+        }
+    }
+    __syncthreads();
+
+    // ---- 7. one thread per cluster: duplicates out, flatness test, Andrew's monotone chain (concurrently)
+    // Cluster c goes to lane c / 4 of warp c % 4: the first four clusters (a scan has three on average) get a warp
+    // each — threads of one warp would execute their data-dependent hull loops one after the other.
     const int nc = min(n_clusters, CL_MAXC);
-    // labels out; from here on LAB[i] is the cluster number of point i (CL_BIG = noise)
-    for (int i = t; i < P; i += CL_THREADS) {
-        const int c = (LAB[i] != CL_BIG) ? CID[LAB[i]] : CL_BIG;
-        labels[(size_t)b * R + RAY[i]] = (c == CL_BIG) ? -1 : c;
-        LAB[i] = c;
-    }
-    if (t < CL_MAXC) { HN[t] = 0; SLOT[t] = -1; CN[t] = 0; CSTART[t] = 0; }
-    __syncthreads();                      // the eps-graph has been read for the last time: its memory becomes MEM / FLG / POS
-    for (int i = t; i < P; i += CL_THREADS) POS[i] = -1;
-    __syncthreads();
-
-    // ---- 6. hulls.  (a) one warp per cluster: member list (ray order), lexicographic extremes, flatness rule
-    {
-        const int warp = t >> 5;
-        int* mem = MEM + warp * Lo.RP;
-        const unsigned lt = (1u << lane) - 1u;
-        int used = 0;                                                      // this warp's lists sit back to back in `mem`
-        for (int c = warp; c < nc; c += CL_WARPS) {
-            int n = 0;
-            for (int base = 0; base < P; base += 32) {
-                const int i = base + lane;
-                const bool ok = i < P && LAB[i] == c;
-                const unsigned m = __ballot_sync(0xffffffffu, ok);
-                if (ok) mem[used + n + __popc(m & lt)] = i;
-                n += __popc(m);
+    const int cl = (t & 31) * (CL_THREADS / 32) + (t >> 5);
+    if (cl < nc) {
+        const int s0 = SEG0[cl], cnt = SEGN[cl] - s0;
+        double* sx = SX + s0;
+        double* sy = SY + s0;
+        int* hull = HULL + s0 + cl;               // cnt + 1 entries are enough; regions of different clusters are disjoint
+        // (this thread works alone while the rest of the block waits at the next barrier — ncu attributed 38 % of the
+        // kernel's stall samples to that wait — so the serial loops below keep what they just touched in registers
+        // instead of re-reading it from shared memory through an index: the top two points of the hull stack, the
+        // last kept point of the duplicate filter)
+        int u = 0;
+        {
+            double lx = 0.0, ly = 0.0;
+            for (int i = 0; i < cnt; ++i) {
+                const double qx = sx[i], qy = sy[i];
+                if (u == 0 || qx != lx || qy != ly) { sx[u] = qx; sy[u] = qy; lx = qx; ly = qy; ++u; }
             }
-            __syncwarp();
-            bool keep = false;
-            if (n >= 3) {
-                // The reference drops a cluster when np.linalg.matrix_rank(points - points[0]) < 2 (`:75-76`) or when
-                // Qhull finds the input flat to its roundoff bound and raises (`:81-83`; ~23 eps max|coordinate|).  Both
-                // only ever trigger on readings taken on ONE straight edge (deviations ~1e-16); real corners deviate by
-                // >= 1e-6.  One test covers both: largest distance from the line through the lexicographic extremes
-                // <= 64 eps max|coordinate|.
-                double lox = INFINITY, loy = INFINITY, hix = -INFINITY, hiy = -INFINITY, scale = 0.0;
-                for (int k = lane; k < n; k += 32) {
-                    const double px = X[mem[used + k]], py = Y[mem[used + k]];
-                    if (lex_less(px, py, lox, loy)) { lox = px; loy = py; }
-                    if (lex_less(hix, hiy, px, py)) { hix = px; hiy = py; }
-                    scale = fmax(scale, fmax(fabs(px), fabs(py)));
-                }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const double ox = __shfl_xor_sync(0xffffffffu, lox, off), oy = __shfl_xor_sync(0xffffffffu, loy, off);
-                    if (lex_less(ox, oy, lox, loy)) { lox = ox; loy = oy; }
-                    const double qx = __shfl_xor_sync(0xffffffffu, hix, off), qy = __shfl_xor_sync(0xffffffffu, hiy, off);
-                    if (lex_less(hix, hiy, qx, qy)) { hix = qx; hiy = qy; }
-                    scale = fmax(scale, __shfl_xor_sync(0xffffffffu, scale, off));
-                }
-                const double dxl = hix - lox, dyl = hiy - loy;
-                double maxcross = 0.0;
-                for (int k = lane; k < n; k += 32)
-                    maxcross = fmax(maxcross, fabs(cross2(dxl, dyl, X[mem[used + k]] - lox, Y[mem[used + k]] - loy)));
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) maxcross = fmax(maxcross, __shfl_xor_sync(0xffffffffu, maxcross, off));
-                const double maxdev = maxcross / sqrt(dxl * dxl + dyl * dyl);      // NaN when all points coincide
-                keep = maxdev > 64.0 * 2.220446049250313e-16 * scale;
-            }
-            if (lane == 0) { CSTART[c] = warp * Lo.RP + used; CN[c] = keep ? n : 0; }
-            used += n;
         }
-    }
-    __syncthreads();
-    // (b) one THREAD per point, all clusters at once: classify against the members of the point's own cluster (every
-    // partner coordinate is read through the member list; neighbouring threads mostly share the cluster)
-    for (int i = t; i < P; i += CL_THREADS) {
-        const int c = LAB[i];
-        int f = 0;
-        if (c < nc && CN[c] > 0) {
-            const int n = CN[c];
-            const int* mem = MEM + CSTART[c];
-            const double xi = X[i], yi = Y[i];
-            bool haveL = false, haveR = false, dup = false;
-            double dnx = 0.0, dny = 0.0, dxx = 0.0, dxy = 0.0;             // min / max angle of p_i - a, a < p_i
-            double enx = 0.0, eny = 0.0, exx = 0.0, exy = 0.0;             // min / max angle of b - p_i, b > p_i
-            for (int a = 0; a < n; ++a) {
-                const int j = mem[a];
-                const double xa = X[j], ya = Y[j];
-                if (xa == xi && ya == yi) { dup = dup || j < i; continue; }       // np.unique: the first copy stays
-                if (lex_less(xa, ya, xi, yi)) {
-                    const double dx = xi - xa, dy = yi - ya;
-                    if (!haveL) { dnx = dxx = dx; dny = dxy = dy; haveL = true; }
-                    else {
-                        if (cross2(dx, dy, dnx, dny) > 0.0) { dnx = dx; dny = dy; }
-                        if (cross2(dxx, dxy, dx, dy) > 0.0) { dxx = dx; dxy = dy; }
+        int h = 0;
+        if (u >= 3) {
+            // The reference drops a cluster when np.linalg.matrix_rank(points - points[0]) < 2 (`:75-76`) or when
+            // Qhull finds the input flat to its roundoff bound and raises (`:81-83`; ~23 eps max|coordinate|).  Both
+            // only ever trigger on readings taken on ONE straight edge (deviations ~1e-16); real corners deviate
+            // by >= 1e-6.  One test covers both: largest distance from the line through the lexicographic
+            // extremes <= 64 eps max|coordinate|.
+            const double dxl = sx[u - 1] - sx[0], dyl = sy[u - 1] - sy[0];
+            const double len = sqrt(dxl * dxl + dyl * dyl);
+            double maxcross = 0.0, scale = 0.0;        // max |cross| = len * max distance: one division, not one per point
+            for (int i = 0; i < u; ++i) {
+                const double ex = sx[i] - sx[0], ey = sy[i] - sy[0];
+                maxcross = fmax(maxcross, fabs(dxl * ey - dyl * ex));
+                scale = fmax(scale, fmax(fabs(sx[i]), fabs(sy[i])));
+            }
+            const double maxdev = maxcross / len;
+            if (maxdev > 64.0 * 2.220446049250313e-16 * scale) {
+                // (ax, ay) / (bx, by): coordinates of hull[h-2] / hull[h-1]; a pop reloads only the new hull[h-2]
+                double ax = 0.0, ay = 0.0, bx = 0.0, by = 0.0;
+                for (int i = 0; i < u; ++i) {
+                    const double qx = sx[i], qy = sy[i];
+                    while (h >= 2) {
+                        const double cr = (bx - ax) * (qy - ay) - (by - ay) * (qx - ax);
+                        if (cr <= 0.0) {
+                            --h; bx = ax; by = ay;
+                            if (h >= 2) { const int a = hull[h - 2]; ax = sx[a]; ay = sy[a]; }
+                        } else break;
                     }
-                } else {
-                    const double ex = xa - xi, ey = ya - yi;
-                    if (!haveR) { enx = exx = ex; eny = exy = ey; haveR = true; }
-                    else {
-                        if (cross2(ex, ey, enx, eny) > 0.0) { enx = ex; eny = ey; }
-                        if (cross2(exx, exy, ex, ey) > 0.0) { exx = ex; exy = ey; }
-                    }
+                    hull[h++] = i;
+                    ax = bx; ay = by; bx = qx; by = qy;
                 }
+                const int lower = h + 1;
+                for (int i = u - 2; i >= 0; --i) {
+                    const double qx = sx[i], qy = sy[i];
+                    while (h >= lower) {
+                        const double cr = (bx - ax) * (qy - ay) - (by - ay) * (qx - ax);
+                        if (cr <= 0.0) {
+                            --h; bx = ax; by = ay;
+                            if (h >= 2) { const int a = hull[h - 2]; ax = sx[a]; ay = sy[a]; }
+                        } else break;
+                    }
+                    hull[h++] = i;
+                    ax = bx; ay = by; bx = qx; by = qy;
+                }
+                --h;                       // the last point repeats the first
+                if (h < 3) h = 0;
             }
-            const bool ext = !haveL || !haveR;
-            const bool lo = !dup && (ext || cross2(dxx, dxy, enx, eny) > 0.0);
-            const bool up = !dup && !lo && cross2(dnx, dny, exx, exy) < 0.0;
-            f = (lo ? 1 : 0) | (up ? 2 : 0);
         }
-        FLG[i] = f;
-    }
-    __syncthreads();
-    // (c) vertex order: counter-clockwise from the lexicographic minimum = lower chain ascending, then upper chain
-    // descending; every vertex counts the vertices of its chain that come before it
-    for (int i = t; i < P; i += CL_THREADS) {
-        const int f = FLG[i];
-        if (!f) continue;
-        const int c = LAB[i], n = CN[c];
-        const int* mem = MEM + CSTART[c];
-        const double xi = X[i], yi = Y[i];
-        int before = 0, n_lo = 0, n_up = 0;
-        for (int a = 0; a < n; ++a) {
-            const int j = mem[a], fj = FLG[j];
-            n_lo += fj & 1;
-            n_up += (fj >> 1) & 1;
-            if (fj == f) before += (f & 1) ? lex_less(X[j], Y[j], xi, yi) : lex_less(xi, yi, X[j], Y[j]);
-        }
-        if (n_lo + n_up >= 3) {
-            POS[i] = (f & 1) ? before : n_lo + before;
-            if ((f & 1) && before == 0) HN[c] = n_lo + n_up;               // the lexicographic minimum reports the size
-        }
+        HN[cl] = h;
     }
     __syncthreads();
 
-    // ---- 7. output slots in cluster order (clusters without a hull are skipped), then every vertex writes itself
-    if (t < 32) {
-        int base = 0;
-        bool ovf = n_clusters > CL_MAXC;
-        for (int c0 = 0; c0 < nc; c0 += 32) {
-            const int c = c0 + lane;
-            const int h = c < nc ? HN[c] : 0;
-            const unsigned m = __ballot_sync(0xffffffffu, h >= 3);
-            if (h >= 3) {
-                const int o = base + __popc(m & ((1u << lane) - 1u));
-                if (o < max_hulls) {
-                    SLOT[c] = o;
-                    hull_nverts[(size_t)b * max_hulls + o] = min(h, max_hull_verts);
-                }
-                ovf = ovf || o >= max_hulls || h > max_hull_verts;
-            }
-            base += __popc(m);
+    // ---- 8. write the hulls in cluster order (clusters without a hull are skipped)
+    int n_out = 0;
+    bool ovf = n_clusters > CL_MAXC;
+    for (int c = 0; c < nc; ++c) {
+        const int h = HN[c];
+        if (h < 3) continue;
+        if (n_out < max_hulls) {
+            const int hv = min(h, max_hull_verts);
+            if (h > max_hull_verts) ovf = true;
+            const int s0 = SEG0[c];
+            const int* hull = HULL + s0 + c;
+            double2* dst = hull_verts + ((size_t)b * max_hulls + n_out) * max_hull_verts;
+            for (int i = t; i < max_hull_verts; i += CL_THREADS)
+                dst[i] = (i < hv) ? make_double2(SX[s0 + hull[i]], SY[s0 + hull[i]]) : make_double2(0.0, 0.0);
+            if (t == 0) hull_nverts[(size_t)b * max_hulls + n_out] = hv;
+            ++n_out;
+        } else {
+            ovf = true;
         }
-        ovf = __any_sync(0xffffffffu, ovf);
-        if (lane == 0) { sOut = min(base, max_hulls); sOvf = ovf ? 1 : 0; }
-    }
-    __syncthreads();
-    const int n_out = sOut;
-    for (int i = t; i < P; i += CL_THREADS) {
-        const int c = LAB[i], q = POS[i];
-        if (c < nc && q >= 0 && q < max_hull_verts && SLOT[c] >= 0)
-            hull_verts[((size_t)b * max_hulls + SLOT[c]) * max_hull_verts + q] = make_double2(X[i], Y[i]);
-    }
-    for (int c = 0; c < nc; ++c) {                                        // zero padding behind every written hull
-        const int o = SLOT[c];
-        if (o < 0) continue;
-        double2* dst = hull_verts + ((size_t)b * max_hulls + o) * max_hull_verts;
-        for (int i = min(HN[c], max_hull_verts) + t; i < max_hull_verts; i += CL_THREADS) dst[i] = make_double2(0.0, 0.0);
     }
     for (int o = n_out + t; o < max_hulls; o += CL_THREADS) hull_nverts[(size_t)b * max_hulls + o] = 0;
-    if (t == 0) { n_hulls[b] = n_out; if (overflow) overflow[b] = sOvf; }
+    if (t == 0) { n_hulls[b] = n_out; if (overflow) overflow[b] = ovf ? 1 : 0; }
 }
 
 }  // namespace ldcbf

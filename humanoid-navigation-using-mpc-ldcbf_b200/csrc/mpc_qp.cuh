@@ -602,7 +602,10 @@ LDCBF_HD void guess_codes(const QpState<N, MO>& s, int (&codes)[2 * N]) {
 // again (at most NV rounds), w = g + N u.  A guess that turns out dependent falls back to the cold start.  The
 // result is exact whatever the guess; a good guess replaces ~15 trips by 2-4.
 // codes[j] = 2*id + (upper side) or -1.  Must be called right after qp_setup (w = g, empty active set).
-template <int N, int MO, int WS>
+// ROLLED: the loop that decodes the guessed rows is not unrolled — one copy in the instruction stream, for the
+// closed-loop kernel that is bound by instruction fetch; the open-loop kernels keep the unrolled form (the race kernel
+// is bound by the latency of one warp's dependent chain: 60 -> 79 us at B = 4096 with the rolled loop).
+template <int N, int MO, int WS, bool ROLLED = false>
 LDCBF_HD void qp_warm_start(const StepConst& C, const int (&codes)[2 * N], double* ws, QpState<N, MO>& s) {
     constexpr int NV = 2 * N;
     if (s.done) return;
@@ -626,12 +629,10 @@ LDCBF_HD void qp_warm_start(const StepConst& C, const int (&codes)[2 * N], doubl
             for (int o = 0; o < MO; ++o) cbf[k * MO + o] = s.ex[o] * s.px[kk] + s.ey[o] * s.py[kk] - s.hb[o];
         }
     }
-    // One copy of the row decoding in the instruction stream (the loop is not unrolled: the kernels that call this every
-    // step are bound by instruction fetch); slot j is addressed dynamically in the workspace, its right-hand side is
-    // parked in the first row of the Gram block, which is only built in the rounds below.
+    // Slot j is addressed dynamically in the workspace, its right-hand side is parked in the first row of the Gram
+    // block, which is only built in the rounds below.
     unsigned mask = 0;
-#pragma unroll 1
-    for (int j = 0; j < NV; ++j) {
+    auto load_row = [&](int j) {
         int code = -1;
 #pragma unroll
         for (int jj = 0; jj < NV; ++jj) if (jj == j) code = codes[jj];
@@ -662,6 +663,13 @@ LDCBF_HD void qp_warm_start(const StepConst& C, const int (&codes)[2 * N], doubl
             GM(0, j) = -sl;
             mask |= 1u << j;
         }
+    };
+    if (ROLLED) {
+#pragma unroll 1
+        for (int j = 0; j < NV; ++j) load_row(j);
+    } else {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) load_row(j);
     }
     double rhs[NV];
 #pragma unroll

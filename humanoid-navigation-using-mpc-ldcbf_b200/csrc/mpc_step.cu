@@ -415,7 +415,7 @@ static int launch_qp(const StepConst& C, int B, int max_obs, const StepIO& io, c
         double* rec = reinterpret_cast<double*>(buf);
         int* ids = reinterpret_cast<int*>(buf + rec_bytes);
         int* count = reinterpret_cast<int*>(buf + rec_bytes + ids_bytes);
-        static const int k0 = env_int("LDCBF_PREP_TRIPS", 2);
+        static const int k0 = env_int("LDCBF_PREP_TRIPS", 3);     // measured at B = 2^20: 0 -> 1.34 ms, 2 -> 1.40, 3 -> 1.21, 4 -> 1.28
         auto prep = k0 <= 0 ? mpc_qp_prepare_kernel<N, MO, BLOCK, 0>
                   : k0 == 1 ? mpc_qp_prepare_kernel<N, MO, BLOCK, 1>
                   : k0 == 2 ? mpc_qp_prepare_kernel<N, MO, BLOCK, 2>

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
 #pragma unroll
                     for (int j = 0; j < 2 * N; ++j) any |= warm[j] >= 0;
                     if (!any) guess_codes<N, MO>(qs, warm);
-                    qp_warm_start<N, MO, BLOCK>(C, warm, ws, qs);
+                    qp_warm_start<N, MO, BLOCK, true>(C, warm, ws, qs);
                 }
                 while (!qs.done) qp_trip<N, MO, BLOCK>(C, ws, qs);
                 qp_finish<N, MO>(C, qs, S);
