@@ -293,6 +293,11 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE line, the JSON result: everything else any library writes to file descriptor 1 (NCCL
+    # prints its version banner there) goes to stderr; the result is written to the saved descriptor at the end
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
     # fork the CPU-baseline workers before this process creates a CUDA context
     port = CpuPort(os.cpu_count() or 1) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
     torch.cuda.set_device(local)
@@ -494,7 +499,8 @@ def run_ours(args):
             if not args.no_extras and "lidar" in line:
                 line["lidar"]["cpu_baseline"] = lidar_reference_baseline(cores)
                 line["roofline_hbm"]["cpu_baseline"] = halfplane_reference_baseline(sc, cores)
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(result_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -587,11 +593,14 @@ def halfplane_reference_baseline(sc, cores, n_scen=512):
                       "ConvexHull objects are built once per scenario outside the count"}
 
 
-def profile_traffic(batch):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, if one exists for this batch."""
+def profile_traffic(key):
+    """dram bytes per launch of a kernel from the committed ncu capture (profiles/kernel_summary.json, written by
+    tools/ncu_traffic.py): key = "rollout" (headline pass) or the batch size of the open-loop K2+K3 solve."""
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "kernel_summary.json")))
-        return prof["k2k3"]["dram_bytes_per_launch"].get(str(batch))
+        if key == "rollout":
+            return prof["rollout"]["dram_bytes_per_launch"]
+        return prof["k2k3"]["dram_bytes_per_launch"].get(str(key))
     except Exception:
         return None
 
