@@ -59,13 +59,21 @@ def retrieve_clusters(points, eps=0.3, min_samples=3):
     return [xy[labels == i] for i in sorted(set(labels.tolist())) if i != -1]
 
 
+EVERYTHING_IS_ONE_CLUSTER = 1e9      # an eps larger than any map: the hull stage of f1 alone (m; squared on the device)
+
+
+def create_convex_hull(cluster):
+    """Hull ring of ONE cluster (reference `:65-83`: np.unique, None for < 3 points or a flat set, else the hull vertices)
+    through the hull stage of the f1 kernel: with min_samples = 1 and an eps that joins every pair the clustering stage
+    returns the input as a single cluster."""
+    _, rings = _cluster(np.asarray(cluster, dtype=np.float64).reshape(-1, 2), eps=EVERYTHING_IS_ONE_CLUSTER, min_samples=1)
+    return rings[0] if rings else None
+
+
 def build_local_obstacles(clusters):
-    out = []
-    for cluster in clusters:
-        _, rings = _cluster(np.asarray(cluster, dtype=np.float64), eps=np.inf if False else 1e9, min_samples=1)
-        if rings:
-            out.append(np.append(rings[0], [rings[0][0]], axis=0))
-    return out
+    """Reference `:119-126`: the hull of every cluster, closed by repeating its first vertex; flat clusters are dropped."""
+    hulls = (create_convex_hull(c) for c in clusters)
+    return [np.append(h, [h[0]], axis=0) for h in hulls if h is not None]
 
 
 def range_finder(lidar_position, obstacles, lidar_range=3.0, resolution=360, noisy=True):

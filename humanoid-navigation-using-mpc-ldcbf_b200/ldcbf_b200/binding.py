@@ -237,27 +237,32 @@ def lidar_cast(pos, verts, nverts, nobs, lidar_range, resolution=360, rays=None)
     return hit_obs, hit_edge, hit_xy
 
 
-def clearance_grid(goal, verts, nverts, nobs, width=250, h_cap=None, with_cost=True):
+def clearance_grid(goal, verts, nverts, nobs, width=250, h_cap=None, with_cost=True, out=None, check=True):
     """f3: occupancy grid + exact distance transform + clearance cost of the planner front-end
     (HumanoidMPCWithRRT.py:21-88,103-108) for a batch of maps.
     Returns dict(meta[B,6] = (min_x, min_y, max_x, max_y, height, occupied cells), og[B,width+1,h_cap+1] uint8,
-    dist, cost[B,width+1,h_cap+1] fp64); cells with j > height are zero.  `h_cap` defaults to 2*width (a frame at
-    most twice as tall as wide); a map that needs more raises."""
+    dist, cost[B,width+1,h_cap+1] fp64); cells with j > height are zero in a fresh result.  `h_cap` defaults to 2*width
+    (a frame at most twice as tall as wide); a map that needs more raises.
+    Hot loops: pass the previous result as `out` (no allocation, no zero fill: cells with j > height then keep whatever
+    an earlier, taller map left there - meta[:, 4] says where the grid ends) and `check=False` (the h_cap check reads a
+    flag back from the device, i.e. synchronises; meta[:, 5] < 0 marks a map that did not fit)."""
     B = goal.shape[0]
     h_cap = int(h_cap) if h_cap is not None else 2 * int(width)
     dev = goal.device
     shape = (B, int(width) + 1, h_cap + 1)
-    out = dict(meta=torch.zeros((B, 6), dtype=F64, device=dev), og=torch.zeros(shape, dtype=torch.uint8, device=dev),
-               dist=torch.zeros(shape, dtype=F64, device=dev),
-               cost=torch.zeros(shape, dtype=F64, device=dev) if with_cost else None)
-    work = torch.empty(shape, dtype=I32, device=dev)
+    if out is None or out["og"].shape != shape or (with_cost and out.get("cost") is None):
+        out = dict(meta=torch.zeros((B, 6), dtype=F64, device=dev), og=torch.zeros(shape, dtype=torch.uint8, device=dev),
+                   dist=torch.zeros(shape, dtype=F64, device=dev),
+                   cost=torch.zeros(shape, dtype=F64, device=dev) if with_cost else None,
+                   work=torch.empty(shape, dtype=I32, device=dev))
     _check(lib().ldcbf_clearance_grid_f64(B, int(width), h_cap, verts.shape[1], verts.shape[2], _ptr(goal, F64, "goal"),
                                           _ptr(verts, F64, "verts"), _ptr(nverts, I32, "nverts"),
                                           _ptr(nobs, I32, "nobs"), _ptr(out["meta"], F64, "meta"),
                                           _ptr(out["og"], torch.uint8, "og"), _ptr(out["dist"], F64, "dist"),
-                                          _ptr(out["cost"], F64, "cost"), _ptr(work, I32, "work"), _stream()),
+                                          _ptr(out["cost"] if with_cost else None, F64, "cost"),
+                                          _ptr(out["work"], I32, "work"), _stream()),
            "ldcbf_clearance_grid_f64")
-    if bool((out["meta"][:, 5] < 0).any()):
+    if check and bool((out["meta"][:, 5] < 0).any()):
         raise ValueError("ldcbf_clearance_grid_f64: a map needs more than h_cap grid rows (or has no obstacle)")
     return out
 

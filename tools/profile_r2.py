@@ -9,7 +9,7 @@ import numpy as np, torch
 import ldcbf_b200 as L
 from ldcbf_b200 import scenarios
 cu = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).cuda()
-REP = 3
+REP = int(os.environ.get("PROFILE_REP", "3"))
 sc = scenarios.config2(4096, seed=0)
 foots = scenarios.foot_window(sc["right_first"], 0, 3)
 prm = L.default_params(0.4)
