@@ -26,6 +26,7 @@ namespace ldcbf {
 
 constexpr int CL_RMAX = 512;
 constexpr int CL_THREADS = 256;
+constexpr int CL_WARPS = CL_THREADS / 32;
 constexpr int CL_BIG = 0x3fffffff;
 
 // Shared-memory layout, sized by RP = R rounded up to 32 (and the sort arrays to the next power of two NS):
@@ -269,77 +270,109 @@ __global__ void __launch_bounds__(CL_THREADS) lidar_clusters_kernel(int R, const
     }
     __syncthreads();
 
-    // ---- 7. one thread per cluster: duplicates out, flatness test, Andrew's monotone chain (concurrently)
-    // Cluster c goes to lane c / 4 of warp c % 4: the first four clusters (a scan has three on average) get a warp
-    // each — threads of one warp would execute their data-dependent hull loops one after the other.
+    // ---- 7. one WARP per cluster: duplicates out, flatness test, both hull chains by parallel elimination
+    // Round 1 ran Andrew's monotone chain in ONE thread per cluster (ncu round 2, source view: 23 k of the 56 k warp
+    // instructions of a scan at 1.1 active lanes, half of the kernel's stall samples on the barrier behind it).  The same
+    // chains, all lanes busy: in a list sorted along x, an interior point that does not make a strict left turn with its
+    // two CURRENT neighbours (the test of the chain: cross(b - a, q - a) <= 0) lies on or below a chord between two
+    // points of the set, so it is not a vertex whatever happens to its neighbours in the same round; every lane tests one
+    // point, the survivors are compacted with a ballot, and the rounds stop when nothing was removed — the survivors then
+    // form a strictly convex chain that contains every vertex: the hull.  A noisy arc halves per round.  Same polygon as
+    // the sequential chain up to which of several points collinear to 1e-16 is kept (different triples are tested).
     const int nc = min(n_clusters, CL_MAXC);
-    const int cl = (t & 31) * (CL_THREADS / 32) + (t >> 5);
-    if (cl < nc) {
-        const int s0 = SEG0[cl], cnt = SEGN[cl] - s0;
-        double* sx = SX + s0;
-        double* sy = SY + s0;
-        int* hull = HULL + s0 + cl;               // cnt + 1 entries are enough; regions of different clusters are disjoint
-        // (this thread works alone while the rest of the block waits at the next barrier — ncu attributed 38 % of the
-        // kernel's stall samples to that wait — so the serial loops below keep what they just touched in registers
-        // instead of re-reading it from shared memory through an index: the top two points of the hull stack, the
-        // last kept point of the duplicate filter)
-        int u = 0;
-        {
-            double lx = 0.0, ly = 0.0;
-            for (int i = 0; i < cnt; ++i) {
-                const double qx = sx[i], qy = sy[i];
-                if (u == 0 || qx != lx || qy != ly) { sx[u] = qx; sy[u] = qy; lx = qx; ly = qy; ++u; }
+    {
+        const int warp = t >> 5;
+        const unsigned lt = (1u << lane) - 1u;
+        for (int cl = warp; cl < nc; cl += CL_WARPS) {
+            const int s0 = SEG0[cl], cnt = SEGN[cl] - s0;
+            const double* sx = SX + s0;
+            const double* sy = SY + s0;
+            int* uniq = LAB + s0;                 // the per-point label arrays are free after step 5 (sorted positions < P)
+            int* hull = HULL + s0 + cl;           // cnt + 1 entries; regions of different clusters are disjoint
+            int* ping = SC + s0;                  // the cluster keys of this segment are all `cl`: free after the boundaries
+            int* pong = CID + s0;
+            // np.unique: a point equal to its predecessor in the sorted segment is dropped
+            int u = 0;
+            for (int base = 0; base < cnt; base += 32) {
+                const int k = base + lane;
+                const bool keep = k < cnt && (k == 0 || sx[k] != sx[k - 1] || sy[k] != sy[k - 1]);
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (keep) uniq[u + __popc(m & lt)] = k;
+                u += __popc(m);
             }
-        }
-        int h = 0;
-        if (u >= 3) {
-            // The reference drops a cluster when np.linalg.matrix_rank(points - points[0]) < 2 (`:75-76`) or when
-            // Qhull finds the input flat to its roundoff bound and raises (`:81-83`; ~23 eps max|coordinate|).  Both
-            // only ever trigger on readings taken on ONE straight edge (deviations ~1e-16); real corners deviate
-            // by >= 1e-6.  One test covers both: largest distance from the line through the lexicographic
-            // extremes <= 64 eps max|coordinate|.
-            const double dxl = sx[u - 1] - sx[0], dyl = sy[u - 1] - sy[0];
-            const double len = sqrt(dxl * dxl + dyl * dyl);
-            double maxcross = 0.0, scale = 0.0;        // max |cross| = len * max distance: one division, not one per point
-            for (int i = 0; i < u; ++i) {
-                const double ex = sx[i] - sx[0], ey = sy[i] - sy[0];
-                maxcross = fmax(maxcross, fabs(dxl * ey - dyl * ex));
-                scale = fmax(scale, fmax(fabs(sx[i]), fabs(sy[i])));
-            }
-            const double maxdev = maxcross / len;
-            if (maxdev > 64.0 * 2.220446049250313e-16 * scale) {
-                // (ax, ay) / (bx, by): coordinates of hull[h-2] / hull[h-1]; a pop reloads only the new hull[h-2]
-                double ax = 0.0, ay = 0.0, bx = 0.0, by = 0.0;
-                for (int i = 0; i < u; ++i) {
-                    const double qx = sx[i], qy = sy[i];
-                    while (h >= 2) {
-                        const double cr = (bx - ax) * (qy - ay) - (by - ay) * (qx - ax);
-                        if (cr <= 0.0) {
-                            --h; bx = ax; by = ay;
-                            if (h >= 2) { const int a = hull[h - 2]; ax = sx[a]; ay = sy[a]; }
-                        } else break;
-                    }
-                    hull[h++] = i;
-                    ax = bx; ay = by; bx = qx; by = qy;
+            __syncwarp();
+            int h = 0;
+            if (u >= 3) {
+                // The reference drops a cluster when np.linalg.matrix_rank(points - points[0]) < 2 (`:75-76`) or when
+                // Qhull finds the input flat to its roundoff bound and raises (`:81-83`; ~23 eps max|coordinate|).  Both
+                // only ever trigger on readings taken on ONE straight edge (deviations ~1e-16); real corners deviate
+                // by >= 1e-6.  One test covers both: largest distance from the line through the lexicographic
+                // extremes <= 64 eps max|coordinate|.
+                const double x0 = sx[uniq[0]], y0 = sy[uniq[0]];
+                const double dxl = sx[uniq[u - 1]] - x0, dyl = sy[uniq[u - 1]] - y0;
+                double maxcross = 0.0, scale = 0.0;
+                for (int k = lane; k < u; k += 32) {
+                    const double px = sx[uniq[k]], py = sy[uniq[k]];
+                    maxcross = fmax(maxcross, fabs(dxl * (py - y0) - dyl * (px - x0)));
+                    scale = fmax(scale, fmax(fabs(px), fabs(py)));
                 }
-                const int lower = h + 1;
-                for (int i = u - 2; i >= 0; --i) {
-                    const double qx = sx[i], qy = sy[i];
-                    while (h >= lower) {
-                        const double cr = (bx - ax) * (qy - ay) - (by - ay) * (qx - ax);
-                        if (cr <= 0.0) {
-                            --h; bx = ax; by = ay;
-                            if (h >= 2) { const int a = hull[h - 2]; ax = sx[a]; ay = sy[a]; }
-                        } else break;
-                    }
-                    hull[h++] = i;
-                    ax = bx; ay = by; bx = qx; by = qy;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    maxcross = fmax(maxcross, __shfl_xor_sync(0xffffffffu, maxcross, off));
+                    scale = fmax(scale, __shfl_xor_sync(0xffffffffu, scale, off));
                 }
-                --h;                       // the last point repeats the first
-                if (h < 3) h = 0;
+                const double maxdev = maxcross / sqrt(dxl * dxl + dyl * dyl);
+                if (maxdev > 64.0 * 2.220446049250313e-16 * scale) {
+                    // one elimination round: src (length m, read through `rev` for the right-to-left chain) -> dst
+                    auto round = [&](const int* src, bool rev, int m, int* dst, bool& changed) {
+                        int out = 0;
+                        changed = false;
+                        for (int base = 0; base < m; base += 32) {
+                            const int j = base + lane;
+                            bool keep = false;
+                            int id = 0;
+                            if (j < m) {
+                                id = src[rev ? m - 1 - j : j];
+                                keep = j == 0 || j == m - 1;
+                                if (!keep) {
+                                    const int ia = src[rev ? m - j : j - 1], iq = src[rev ? m - 2 - j : j + 1];
+                                    const double ax = sx[ia], ay = sy[ia];
+                                    keep = (sx[id] - ax) * (sy[iq] - ay) - (sy[id] - ay) * (sx[iq] - ax) > 0.0;
+                                }
+                            }
+                            const unsigned mk = __ballot_sync(0xffffffffu, keep);
+                            if (keep) dst[out + __popc(mk & lt)] = id;
+                            out += __popc(mk);
+                            changed = changed || mk != __ballot_sync(0xffffffffu, j < m);
+                        }
+                        __syncwarp();
+                        return out;
+                    };
+                    bool changed;
+                    // lower chain, left to right: uniq -> hull -> ping -> hull ...; ends in `hull`
+                    int m = round(uniq, false, u, hull, changed);
+                    while (changed) {
+                        m = round(hull, false, m, ping, changed);
+                        for (int k = lane; k < m; k += 32) hull[k] = ping[k];
+                        __syncwarp();
+                    }
+                    const int n_lo = m;
+                    // upper chain, right to left: uniq reversed -> ping -> pong -> ping ...; ends in `ping`
+                    m = round(uniq, true, u, ping, changed);
+                    while (changed) {
+                        m = round(ping, false, m, pong, changed);
+                        for (int k = lane; k < m; k += 32) ping[k] = pong[k];
+                        __syncwarp();
+                    }
+                    // counter-clockwise: the lower chain, then the upper chain without its two end points
+                    for (int k = 1 + lane; k < m - 1; k += 32) hull[n_lo + k - 1] = ping[k];
+                    h = n_lo + m - 2;
+                    if (h < 3) h = 0;
+                    __syncwarp();
+                }
             }
+            if (lane == 0) HN[cl] = h;
         }
-        HN[cl] = h;
     }
     __syncthreads();
 

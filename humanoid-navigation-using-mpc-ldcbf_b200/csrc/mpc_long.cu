@@ -81,7 +81,8 @@ __host__ __device__ inline size_t long_carve(int N, int max_obs, char* base, Lon
 struct LongScalars {
     double p0x, p0y, v0x, v0y, gx, gy, delta, vlat_mid, vlat_half;
     double rx, ry, nn, s_p, u_p, t, t1, d2n2;
-    int q, status, iters, done, typ, k, code, full, dep, l, inner_done;
+    double tol;       // a row counts as violated below -tol: eps_active, eps_infeasible after the relaxed restart
+    int q, status, iters, done, typ, k, code, full, dep, l, inner_done, restart;
 };
 
 // Slack (natural units), deviation sign and 1/|normal| of row `row` at the current iterate.
@@ -207,6 +208,7 @@ __global__ void __launch_bounds__(T, MINB) mpc_long_kernel(StepConst C, int B, i
                 S.vinrm[k + 1] = 1.0 / (C.gtil * sqrt((double)(4 * k + 1)));   // |vel row k+1| = gtil sqrt(4(k+1)-3)
             }
             sc.status = LDCBF_STATUS_SOLVED; sc.iters = 0; sc.q = 0; sc.done = 0;
+            sc.tol = C.eps_active; sc.restart = 0;
         }
         if (io.state6) {
             const int f0 = io.state6[6 * (size_t)b + 5] < 0.0 ? -1 : 1;
@@ -243,6 +245,17 @@ __global__ void __launch_bounds__(T, MINB) mpc_long_kernel(StepConst C, int B, i
         // ------------------------------------------------------------------ active-set loop
         PROF(1)
         while (!sc.done) {
+            if (sc.restart) {
+                // relaxed restart (same rule as mpc_qp.cuh:qp_trip): back to the empty active set at w = (g, .., g)
+                for (int i = tid; i < n * ld; i += T) S.J[i] = 0.0;
+                for (int i = tid; i < long_rsize(n); i += T) S.R[i] = 0.0;
+                for (int i = tid; i < nrows; i += T) S.act[i] = 0;
+                __syncthreads();
+                for (int k = 1 + tid; k <= N; k += T) { S.P[2 * k] = sc.gx; S.P[2 * k + 1] = sc.gy; }
+                for (int i = tid; i < n; i += T) { S.J[i * ld + i] = 1.0; S.u[i] = 0.0; }
+                if (tid == 0) { sc.q = 0; sc.restart = 0; }
+                __syncthreads();
+            }
             // velocities at the iterate
             long_velocities<T>(N, C.gtil, S, sc);
             __syncthreads();
@@ -281,7 +294,7 @@ __global__ void __launch_bounds__(T, MINB) mpc_long_kernel(StepConst C, int B, i
             if (tid == 0) {
                 for (int w = 1; w < T / 32; ++w)
                     if (S.redv[w] < best || (S.redv[w] == best && S.redi[w] < bid)) { best = S.redv[w]; bid = S.redi[w]; }
-                if (!(best < -C.eps_active)) sc.done = 1;
+                if (!(best < -sc.tol)) sc.done = 1;
                 else {
                     double sl, m, inrm;
                     long_eval_row(bid, N, nobs, S, C, sc, sl, m, inrm);
@@ -408,7 +421,13 @@ __global__ void __launch_bounds__(T, MINB) mpc_long_kernel(StepConst C, int B, i
                     const bool full = !dep && (l < 0 || t2 <= sc.t1);
                     sc.full = full; sc.dep = dep;
                     if (it > iter_cap) { sc.status = LDCBF_STATUS_MAX_ITER; sc.done = 1; sc.inner_done = 1; }
-                    else if (!full && l < 0) { sc.status = LDCBF_STATUS_INFEASIBLE; sc.done = 1; sc.inner_done = 1; }
+                    else if (!full && l < 0) {
+                        if (sc.tol < C.eps_infeasible && -sc.s_p <= C.eps_infeasible) {
+                            sc.tol = C.eps_infeasible; sc.restart = 1; sc.inner_done = 1;     // feasible set = a point to rounding
+                        } else {
+                            sc.status = LDCBF_STATUS_INFEASIBLE; sc.done = 1; sc.inner_done = 1;
+                        }
+                    }
                     else {
                         const double t = full ? t2 : sc.t1;
                         sc.t = t;

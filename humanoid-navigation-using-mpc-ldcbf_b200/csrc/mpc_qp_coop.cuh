@@ -82,6 +82,7 @@ struct CoopState {
     int q;
     int status, iters;
     bool need_scan, done;
+    double tol;              // a row counts as violated below -tol (eps_active; eps_infeasible after a relaxed restart)
     double p0x, p0y, v0x, v0y, gx, gy;
     double th[N + 1], om[N];
 #ifdef LDCBF_COOP_PROFILE
@@ -205,6 +206,7 @@ LDCBF_HD void coop_setup(const StepConst& C, const LaneGroup<G>& grp, double p0x
     }
     s.nn = 1.0; s.s_p = 0.0; s.u_p = 0.0; s.p_code = 0; s.q = 0;
     s.iters = 0; s.need_scan = true;
+    s.tol = C.eps_active;
     s.status = status;
     s.done = status != LDCBF_STATUS_SOLVED;
     grp.sync();
@@ -243,7 +245,7 @@ LDCBF_HD void coop_trip(const StepConst& C, const LaneGroup<G>& grp, const doubl
         for (int c = 0; c < NV; ++c) { a[c] = CA(c, id); m += a[c] * s.w[c]; }
         const bool two = id < 4 * N;
         const double sl = two ? CA(NV + 1, id) - fabs(m) : m;
-        if (!(sl < -C.eps_active)) { s.done = true; return; }     // primal feasible: optimal
+        if (!(sl < -s.tol)) { s.done = true; return; }     // primal feasible: optimal
         const double sg = upper ? -1.0 : 1.0;
         double nn = 0.0;
 #pragma unroll
@@ -299,7 +301,24 @@ LDCBF_HD void coop_trip(const StepConst& C, const LaneGroup<G>& grp, const doubl
     const double t1n = tn[0], t1d = td[0];
     const int ldrop = tj[0];
     const bool full = !dependent && (ldrop < 0 || (-s.s_p) * t1d <= t1n * zz);
-    if (!full && ldrop < 0) { s.status = LDCBF_STATUS_INFEASIBLE; s.done = true; return; }
+    if (!full && ldrop < 0) {
+        // same rule as mpc_qp.cuh:qp_trip — a row that cannot be satisfied but is violated by no more than eps_infeasible
+        // (a feasible set that is a point to rounding) restarts the solve once with that tolerance
+        if (s.tol < C.eps_infeasible && -s.s_p <= C.eps_infeasible) {
+            s.tol = C.eps_infeasible;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) { s.J[i][j] = (i == j) ? 1.0 : 0.0; s.R[i][j] = (i == j) ? 1.0 : 0.0; }
+                s.Rinv[j] = 1.0; s.u[j] = 0.0; s.code[j] = -1; s.np[j] = 0.0;
+                s.w[j] = (j & 1) ? s.gy : s.gx;
+            }
+            s.nn = 1.0; s.s_p = 0.0; s.u_p = 0.0; s.p_code = 0; s.q = 0;
+            s.need_scan = true;
+            return;
+        }
+        s.status = LDCBF_STATUS_INFEASIBLE; s.done = true; return;
+    }
     COOP_T(2);
     const double t = full ? (-s.s_p) / zz : t1n / t1d;
 #pragma unroll
