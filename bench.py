@@ -50,7 +50,7 @@ def make_config(batch_per_gpu):
     """The `config` object of the JSON line — identical on both arms (the driver compares them)."""
     return {"workload": WORKLOAD, "batch_per_gpu": batch_per_gpu, "horizon": N_HORIZON, "obstacles": 3,
             "max_steps": MAX_STEPS, "ldcbf_margin": MARGIN, "seed": 0,
-            "sharding": "one seeded batch of batch_per_gpu x n_gpus scenarios, contiguous shard per rank",
+            "sharding": "one seeded batch of batch_per_gpu x n_gpus scenarios (block i = generator seed i), contiguous shard per rank",
             "l2": "flushed (256 MB write) between timed passes on the GPU arm"}
 # algorithmic flop model of the fused step kernel at (N, n_obs) = (3, 3), DESIGN.md §6
 FLOP_PER_ITER = 470.0
@@ -307,10 +307,10 @@ def run_ours(args):
     L.lib()
     Bg, N = args.batch, N_HORIZON
     B_total = Bg * world
-    # ONE seeded batch for the whole job, contiguous shard per rank; the generator is sequential, so
-    # every rank draws the same B_total scenarios and keeps its slice: no data moves between ranks
+    # ONE seeded batch for the whole job, contiguous shard per rank: block i of the batch is
+    # config2(batch, seed = i), so a rank draws only the blocks its shard touches and no data moves between ranks
     lo, hi = sharding.shard_bounds(B_total, world, rank)
-    sc = shard_of(scenarios.config2(B_total, seed=0), lo, hi)
+    sc = scenarios.config2_sharded(B_total, lo, hi, seed=0, block=Bg)
     B = hi - lo
     foots = scenarios.foot_window(sc["right_first"], 0, N)
     d = device_inputs(sc, foots, torch)

@@ -243,23 +243,28 @@ __global__ void __launch_bounds__(CL_THREADS) lidar_clusters_kernel(int R, const
     if (t < CL_MAXC) { SEG0[t] = 0; SEGN[t] = 0; HN[t] = 0; }
     __syncthreads();
 
-    // ---- 6. ONE bitonic sort by (cluster, x, y): every cluster becomes a contiguous, np.unique-ordered segment
+    // ---- 6. ONE bitonic sort by (cluster, x, y): every cluster becomes a contiguous, np.unique-ordered segment.
+    // Work items are the ns / 2 compare-exchange pairs of a stage; pair q of a stage with partner distance j touches
+    // i = 2j (q / j) + q % j and i + j.  For j <= 32 both lie in the 64-element chunk q / 32, which belongs to one warp:
+    // those stages only need a warp barrier (3 block barriers instead of 36 at ns = 256).
     for (int k = 2; k <= ns; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = t; i < ns; i += CL_THREADS) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const bool up = (i & k) == 0;
-                    const int ac = SC[i], bc = SC[l];
-                    const double ax = SX[i], ay = SY[i], bx = SX[l], by = SY[l];
-                    if (key_less(bc, bx, by, ac, ax, ay) == up) {
-                        SC[i] = bc; SX[i] = bx; SY[i] = by; SC[l] = ac; SX[l] = ax; SY[l] = ay;
-                    }
+            for (int q = t; q < (ns >> 1); q += CL_THREADS) {
+                const int i = 2 * j * (q / j) + (q % j), l = i + j;
+                const bool up = (i & k) == 0;
+                const int ac = SC[i], bc = SC[l];
+                const double ax = SX[i], ay = SY[i], bx = SX[l], by = SY[l];
+                if (key_less(bc, bx, by, ac, ax, ay) == up) {
+                    SC[i] = bc; SX[i] = bx; SY[i] = by; SC[l] = ac; SX[l] = ax; SY[l] = ay;
                 }
             }
-            __syncthreads();
+            // the NEXT stage has distance j / 2 (or k for the first stage of the next k): a block barrier is needed
+            // whenever this stage or the next one crosses 64-element chunks
+            const int jn = (j > 1) ? (j >> 1) : k;
+            if (j > 32 || jn > 32) __syncthreads(); else __syncwarp();
         }
     }
+    __syncthreads();
     // segment boundaries
     for (int i = t; i < ns; i += CL_THREADS) {
         const int c = SC[i];

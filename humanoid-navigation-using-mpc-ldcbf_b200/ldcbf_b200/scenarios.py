@@ -91,6 +91,23 @@ def config2(B=4096, seed=0):
     return dict(state=state, goal=goal, right_first=right, verts=verts, nverts=nverts, nobs=nobs, rings=rings_all)
 
 
+def config2_sharded(B_total, lo, hi, seed=0, block=4096):
+    """Scenarios [lo, hi) of the multi-GPU config-2 batch: the concatenation of config2(block, seed + i), i = 0, 1, ...
+    (block i holds scenarios [i*block, (i+1)*block)), so a rank only draws the blocks its shard touches and the first
+    `block` scenarios are exactly config2(block, seed)."""
+    parts = []
+    for i in range(lo // block, (min(hi, B_total) - 1) // block + 1):
+        n = min(block, B_total - i * block)
+        sc = config2(n, seed=seed + i)
+        a, b = max(lo, i * block) - i * block, min(hi, i * block + n) - i * block
+        parts.append({k: v[a:b] for k, v in sc.items()})
+    out = {}
+    for k in parts[0]:
+        v = [p[k] for p in parts]
+        out[k] = sum(v, []) if isinstance(v[0], list) else np.concatenate(v, axis=0)
+    return out
+
+
 def foot_window(right_first, step, N):
     """Parity window s_v[step:step+N+1] of HumanoidMpc.py:104-108,403 for arrays of scenarios -> int8[B,N+1]."""
     right_first = np.asarray(right_first, dtype=bool)
