@@ -15,11 +15,14 @@
 //     points in index order and opens a cluster at the first unvisited core point);
 //   * a border point takes the lowest-numbered cluster among its core neighbours (it is labelled by the first
 //     cluster that reaches it and never relabelled); everything else is noise (-1).
-// The eps-graph is held as a bit matrix in shared memory (R x R/32 words), components by min-label propagation.
+// The eps-graph is held as a bit matrix in shared memory (R x R/32 words); components: every core point first takes its
+// lowest-indexed core neighbour (one find-first-set), chases that pointer to a root, and min-label propagation sweeps
+// then confirm the fixed point.
 // Hulls: ONE bitonic sort of all clustered points by (cluster, x, y) turns every cluster into a contiguous segment in
-// np.unique order; then one thread per cluster removes duplicates, tests flatness and runs Andrew's monotone chain
-// (counter-clockwise, strictly convex), all clusters concurrently.  Qhull and the chain may disagree on which of
-// several points that are collinear to 1e-16 is called a vertex; the polygons are the same to rounding.
+// np.unique order; then one WARP per cluster removes duplicates (ballot compaction), tests flatness (warp reduction) and
+// builds both chains of Andrew's monotone-chain hull by parallel elimination (step 7), all clusters concurrently.  Qhull
+// and the chain may disagree on which of several points that are collinear to 1e-16 is called a vertex; the polygons are
+// the same to rounding.
 #include "ldcbf_common.cuh"
 
 namespace ldcbf {
