@@ -677,23 +677,25 @@ LDCBF_HD void qp_warm_start(const StepConst& C, const int (&codes)[2 * N], doubl
     if (mask == 0u) return;
     bool fail = false;
     double uu[NV];
-    for (int round = 0; round <= NV; ++round) {
-        ++s.iters;      // a round costs about one trip (Gram matrix, Cholesky, two solves) and is counted as one
-        // Gram matrix of the loaded slots (identity on the empty ones), Cholesky, u = G^-1 rhs
-        double L[NV][NV];
+    // Gram matrix of the loaded slots (identity on the empty ones), once: a round that drops rows only has to put the
+    // identity back on their rows and columns, the entries between the rows that stay do not change
 #pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            const bool aj = (mask >> j) & 1u;
+    for (int j = 0; j < NV; ++j) {
+        const bool aj = (mask >> j) & 1u;
 #pragma unroll
-            for (int l = 0; l <= j; ++l) {
-                double g2 = 0.0;
+        for (int l = 0; l <= j; ++l) {
+            double g2 = 0.0;
 #pragma unroll
-                for (int i = 0; i < NV; ++i) g2 += AN(j, i) * AN(l, i);
-                const bool al = (mask >> l) & 1u;
-                g2 = (aj && al) ? g2 : (j == l ? 1.0 : 0.0);
-                GM(j, l) = g2; GM(l, j) = g2;
-            }
+            for (int i = 0; i < NV; ++i) g2 += AN(j, i) * AN(l, i);
+            const bool al = (mask >> l) & 1u;
+            g2 = (aj && al) ? g2 : (j == l ? 1.0 : 0.0);
+            GM(j, l) = g2; GM(l, j) = g2;
         }
+    }
+    for (int round = 0; round <= NV; ++round) {
+        ++s.iters;      // a round costs about one trip (Cholesky, two solves) and is counted as one
+        // Cholesky, u = G^-1 rhs
+        double L[NV][NV];
         bool indep = true;      // every pivot above 1e-10 of its diagonal entry (compared without the division)
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
@@ -737,7 +739,8 @@ LDCBF_HD void qp_warm_start(const StepConst& C, const int (&codes)[2 * N], doubl
         for (int j = 0; j < NV; ++j) {
             if ((neg >> j) & 1u) {
 #pragma unroll
-                for (int i = 0; i < NV; ++i) AN(j, i) = 0.0;
+                for (int i = 0; i < NV; ++i) { AN(j, i) = 0.0; GM(j, i) = 0.0; GM(i, j) = 0.0; }
+                GM(j, j) = 1.0;
                 RC(j) = -1.0;
             }
         }
