@@ -17,7 +17,7 @@ for k in ks:
         out["k2k3"]["dram_bytes_per_launch"]["4096"] = b
     if "mpc_qp_prepare_kernel" in name or ("mpc_qp_refill_kernel" in name):
         k2k3_big += b
-    if "halfplane_kernel" in name:
+    if "halfplane_kernel" in name and grid >= 8192:          # the B = 2^20 launch (the driver also runs K1 on small batches)
         out["halfplane_kernel"] = {"dram_bytes_per_launch": b, "batch": 1 << 20}
 if k2k3_big:
     out["k2k3"]["dram_bytes_per_launch"][str(1 << 20)] = k2k3_big
