@@ -547,7 +547,8 @@ def config4_sharded(L, sharding, world, rank, torch, dist, allreduce, sync_all, 
     rows = torch.cat((state, r["steps"].double()[:, None], r["status"].double()[:, None],
                       r["goal_steps"].double()), dim=1).contiguous()
     if world > 1:
-        allrows = sharding.gather_results(rows, B_total)
+        for _ in range(2):
+            allrows = sharding.gather_results(rows, B_total)
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
