@@ -479,7 +479,7 @@ def run_ours(args):
             line["unknown_env_rollout"] = unknown_env_rollout_bench(L, torch)
             line["latency_b1"] = latency_b1(L, torch)
             line["bounds_tuning"] = bounds_tuning_bench(torch)
-            line["long_horizon"] = long_horizon_bench(L, torch)
+            line["long_horizon"] = long_horizon_bench(L, torch, peak_fp64)
             line["clearance_grid"] = clearance_bench(L, torch)
     if clk:
         clk.__exit__()
@@ -832,14 +832,20 @@ def latency_b1(L, torch, n=200):
                     "CasADi/IPOPT per step, not measurable offline"}
 
 
-def long_horizon_bench(L, torch):
-    """Config 5 (scaling sweep) samples: one open-loop MPC step per scenario at horizon 10 / 20 / 40 with 8 / 16 / 64
-    octagonal obstacles, solved by the block-per-scenario kernel (csrc/mpc_long.cu)."""
+def long_horizon_bench(L, torch, peak_fp64=None):
+    """Config 5 (scaling sweep): one open-loop MPC step per scenario over the grid horizon {10, 20, 40} x obstacles
+    {8, 16, 32, 64}, solved by the block-per-scenario kernel (csrc/mpc_long.cu); batch sized to one wave of resident
+    blocks and above.  Flop model of one active-set iteration with n = 2N unknowns and q active rows:
+    d = J^T n+ (2n * 2k nonzeros <= 2n^2/2), r = R^-1 d (q^2), z = J2 d2 (2n(n-q)), Householder on the free columns
+    (4n(n-q)) or a Givens chain (6n(q-l)), scan of 4N + N*n_obs rows (~12 flop each): about 5n^2 + 12(4N + N n_obs)."""
     from ldcbf_b200 import scenarios
     cu = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).cuda()
     prm = L.default_params(0.4)
     rows = []
-    for N, n_obs, B in ((10, 8, 8192), (20, 16, 4096), (40, 64, 1184)):
+    grid = [(N, n_obs) for N in (10, 20, 40) for n_obs in (8, 16, 32, 64)]
+    batch = {10: 8192, 20: 4096, 40: 1184}
+    for N, n_obs in grid:
+        B = batch[N]
         sc = scenarios.config5(B, n_obs, seed=0)
         foots = scenarios.foot_window(sc["right_first"], 0, N)
         args = (prm, cu(sc["state"][:, :4]), cu(sc["state"][:, 4]), cu(sc["goal"]), cu(foots, torch.int8),
@@ -856,10 +862,17 @@ def long_horizon_bench(L, torch):
             ts.append(e0.elapsed_time(e1))
         ms = statistics.median(ts)
         st = out["status"]
-        rows.append({"horizon": N, "obstacles": n_obs, "batch": B, "ms": ms, "value": B / (ms * 1e-3), "unit": UNIT,
-                     "solved": int((st == 0).sum().item()), "infeasible": int((st == 2).sum().item()),
-                     "iteration_cap": int((st == 1).sum().item()),
-                     "mean_iterations": float(out["iters"].double().mean().item())})
+        it = float(out["iters"].double().sum().item())
+        n = 2 * N
+        flops = it * (5.0 * n * n + 12.0 * (4 * N + N * n_obs))
+        row = {"horizon": N, "obstacles": n_obs, "batch": B, "ms": ms, "value": B / (ms * 1e-3), "unit": UNIT,
+               "solved": int((st == 0).sum().item()), "infeasible": int((st == 2).sum().item()),
+               "iteration_cap": int((st == 1).sum().item()), "mean_iterations": it / B}
+        if peak_fp64:
+            ach = flops / (ms * 1e-3) / 1e12
+            row["roofline"] = {"bound": "fp64", "kernel": "mpc_long_kernel", "achieved": ach, "peak": peak_fp64,
+                               "unit": "TFLOP/s", "frac": ach / peak_fp64}
+        rows.append(row)
     return rows
 
 

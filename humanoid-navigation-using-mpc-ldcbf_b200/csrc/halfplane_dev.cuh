@@ -8,7 +8,8 @@
 //  * EXACT = true (default of the library): every operation is an explicit round-to-nearest intrinsic in the
 //    order of oracle/halfplane.py — including numpy's fma(a1, b1, a0*b0) 2-element dot, sqrt(dot)**2 for
 //    np.power(np.linalg.norm(AB), 2) and the rounded distance in the `dist < min_dist` test — so (c, eta) are
-//    bit-equal to the reference.  This matters in closed loop: an active LDCBF row puts the next CoM exactly on
+//    bit-equal to the oracle, which applies the reference's per-edge arithmetic along the hull ring (the reference
+//    walks ConvexHull.simplices: another edge order, results equal to ~1e-13).  This matters in closed loop: an active LDCBF row puts the next CoM exactly on
 //    an obstacle edge, where eta = (x - c)/||x - c|| is decided by the last bits of the arithmetic.
 //  * EXACT = false (LDCBF_FLAG_FAST_GEOMETRY): same algorithm to ~1 ulp with one reciprocal instead of two
 //    square roots and a division per edge and squared-distance comparisons; 1.8x fewer FP64 instructions.

@@ -198,6 +198,10 @@ static int launch_rollout(const StepConst& C, int B, int T, int n_goals, int msg
     // at different places in its code: the time then goes to instruction fetch).
     if (B < 148 * 4 * 16 && max_verts > 8) {
         static const int rb = getenv("LDCBF_ROLLOUT_BLOCK") ? atoi(getenv("LDCBF_ROLLOUT_BLOCK")) : 32;
+        static const int rg = getenv("LDCBF_ROLLOUT_G") ? atoi(getenv("LDCBF_ROLLOUT_G")) : 4;
+        if (!io.fast_geometry && rg == 1) return launch_rollout_block<N, MO, true, 32, 1>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
+        if (!io.fast_geometry && rg == 2) return launch_rollout_block<N, MO, true, 32, 2>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
+        if (!io.fast_geometry && rg == 8) return launch_rollout_block<N, MO, true, 32, 8>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
         if (!io.fast_geometry && rb == 8) return launch_rollout_block<N, MO, true, 8, 4>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
         if (!io.fast_geometry && rb == 16) return launch_rollout_block<N, MO, true, 16, 4>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
         return io.fast_geometry ? launch_rollout_block<N, MO, false, 32, 4>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st)

@@ -82,7 +82,9 @@ typedef struct ldcbf_params {
                                solve is repeated with rows counted as violated only below -eps_infeasible (ABI 2) */
 } ldcbf_params;
 
-/* flags.  Default 0: the half-plane builder restates the reference's arithmetic bit for bit.
+/* flags.  Default 0: the half-plane builder restates the reference's per-edge arithmetic operation by operation (it walks
+ * the hull ring in vertex order where the reference iterates ConvexHull.simplices: (c, eta) equal the reference's to
+ * ~1e-13, and are bit-equal to the ring-order oracle).
  * FAST_GEOMETRY trades that for ~1 ulp agreement (one reciprocal instead of two square roots and a division per
  * edge); use it only when bit parity of (c, eta) with the reference is not needed. */
 #define LDCBF_FLAG_FAST_GEOMETRY 1
