@@ -12,12 +12,20 @@
 // Mapping: one thread per scenario, persistent over all its steps: no per-step launch latency, the
 // scenario's vertex rings stay in L1/L2 (832 B at the basic shape), state and active data in registers.
 // Scenarios are independent, so a block never synchronises.
+#include <cstdio>
 #include <cstdlib>
 
 #include "halfplane_dev.cuh"
 #include "mpc_qp.cuh"
 
 namespace ldcbf {
+
+// development aid (make profile-lib): cycles per phase of a loop step, accumulated by thread 0 of block 0 and printed
+#if defined(LDCBF_ROLLOUT_PROFILE) && defined(__CUDA_ARCH__)
+#define RO_T(k) do { const long long now_ = clock64(); prof_[k] += now_ - prof_t_; prof_t_ = now_; } while (0)
+#else
+#define RO_T(k) do { } while (0)
+#endif
 
 struct RolloutIO {
     double* state; const double* goals; const int8_t* right_first; const double2* verts; const int32_t* nverts;
@@ -27,6 +35,7 @@ struct RolloutIO {
     // ABI 2: half-planes of the obstacles beyond the MO register-resident ones ([B,max_obs] double4, library-owned
     // scratch), iteration counter, per-scenario reason the loop ended (LDCBF_END_*)
     double4* ce_scratch; unsigned long long* total_iters; int32_t* end_code;
+    int start_mode;   // development switch LDCBF_ROLLOUT_START: 0 shifted active set (default), 1 geometric guess every step
 };
 
 // G lanes per scenario (small batches): the kernel time is the slowest scenario's chain of sequential steps, and a
@@ -56,6 +65,9 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
     double* tU = (io.traj_U && writer) ? io.traj_U + (size_t)b * T * 3 : nullptr;
     if (tX) { tX[0] = px; tX[1] = vx; tX[2] = py; tX[3] = vy; tX[4] = th; }
 
+#if defined(LDCBF_ROLLOUT_PROFILE) && defined(__CUDA_ARCH__)
+    long long prof_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, prof_t_ = clock64();
+#endif
     int gi = 0, kstep = 0, total = 0, solves = 0, iters_sum = 0, last_status = LDCBF_STATUS_SOLVED;
     int end_code = LDCBF_END_BUDGET;
     int warm[2 * N];                       // active set of the previous step, shifted by one stage (-1: none)
@@ -82,6 +94,7 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
         }
         const double gx = io.goals[((size_t)b * n_goals + gi) * 2], gy = io.goals[((size_t)b * n_goals + gi) * 2 + 1];
         double th1, om0;
+        RO_T(0);
         if (n_goals > 1 && kstep + 1 >= max_steps_per_goal) {      // last step of a run: park the state before it (lanes
             io.state[5 * (size_t)b] = px; io.state[5 * (size_t)b + 1] = vx; io.state[5 * (size_t)b + 2] = py;   // of a group
             io.state[5 * (size_t)b + 3] = vy; io.state[5 * (size_t)b + 4] = th;                  // store equal values)
@@ -102,6 +115,7 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
             double4 ce[MO];
 #pragma unroll
             for (int o = 0; o < MO; ++o) ce[o] = (o < nb) ? ces[o] : make_double4(0.0, 0.0, 0.0, 0.0);
+            RO_T(1);
             int ft[N + 1];
             const int step_number = kstep / substeps;                                 // :401
 #pragma unroll
@@ -111,16 +125,20 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
                 QpState<N, MO> qs;
                 double* ws = qp_ws + threadIdx.x;
                 qp_setup<N, MO, BLOCK>(C, px, vx, py, vy, th, gx, gy, ft, ce, nb, ces + MO, n_stream, dl, lim, ws, qs);
+                RO_T(2);
                 if (io.warm_start) {
                     bool any = false;                       // nothing carried over (first step of a run): geometric guess
 #pragma unroll
                     for (int j = 0; j < 2 * N; ++j) any |= warm[j] >= 0;
-                    if (!any) guess_codes<N, MO>(qs, warm);
+                    if (!any || io.start_mode == 1) guess_codes<N, MO>(qs, warm);
                     qp_warm_start<N, MO, BLOCK, true>(C, warm, ws, qs);
                 }
+                RO_T(3);
                 while (!qs.done) qp_trip<N, MO, BLOCK>(C, ws, qs);
+                RO_T(4);
                 qp_finish<N, MO>(C, qs, S);
                 shift_codes<N, MO, BLOCK>(qs, ws, warm);
+                RO_T(5);
             }
             solves += writer ? 1 : 0;
             iters_sum += writer ? S.iters : 0;
@@ -155,6 +173,11 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
         ++total; ++kstep;
         if (tX) { double* x = tX + 5 * total; x[0] = px; x[1] = vx; x[2] = py; x[3] = vy; x[4] = th; }
     }
+#if defined(LDCBF_ROLLOUT_PROFILE) && defined(__CUDA_ARCH__)
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        printf("rollout profile (cycles, thread 0): steps %d iters %d | loop %lld K1 %lld setup %lld warm %lld trips %lld finish %lld\n",
+               total, iters_sum, prof_[0], prof_[1], prof_[2], prof_[3], prof_[4], prof_[5]);
+#endif
     if (writer) {
         if (gi < n_goals) io.goal_steps[(size_t)b * n_goals + gi] = kstep;
         io.state[5 * (size_t)b] = px; io.state[5 * (size_t)b + 1] = vx; io.state[5 * (size_t)b + 2] = py;
@@ -256,7 +279,8 @@ extern "C" int ldcbf_rollout_f64(const ldcbf_params* prm, int B, int N, int T, i
                        traj_X, traj_U, steps, goal_steps, status,
                        reinterpret_cast<unsigned long long*>(total_solves),
                        (prm->flags & LDCBF_FLAG_FAST_GEOMETRY) != 0, (prm->flags & LDCBF_FLAG_COLD_START) == 0,
-                       scratch, reinterpret_cast<unsigned long long*>(total_iters), end_code};
+                       scratch, reinterpret_cast<unsigned long long*>(total_iters), end_code,
+                       getenv("LDCBF_ROLLOUT_START") ? atoi(getenv("LDCBF_ROLLOUT_START")) : 0};
     int rc;
     switch (N) {
         case 1: rc = dispatch_rollout<1>(C, B, T, n_goals, max_steps_per_goal, sub, max_obs, max_verts, io, st); break;

@@ -19,8 +19,10 @@ for _ in range(10):
     st = st0.clone(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); r = eng.rollout(st, rf, 150, record=False); e1.record(); e1.synchronize(); ts.append(e0.elapsed_time(e1))
 print(json.dumps({"block": os.environ.get("LDCBF_ROLLOUT_BLOCK"), "G": os.environ.get("LDCBF_ROLLOUT_G"), "ms": statistics.median(ts), "solves": int(r["total_solves"].item()),
-                  "steps_sum": int(r["steps"].sum().item())}))
+                  "steps_sum": int(r["steps"].sum().item()), "start": os.environ.get("LDCBF_ROLLOUT_START"),
+                  "iters_mean": float(r["total_iters"].item()) / int(r["total_solves"].item())}))
 ''' % ROOT
 for blk in sys.argv[1:] or ["32", "16", "8"]:
-    env = dict(os.environ, LDCBF_ROLLOUT_BLOCK=blk) if not blk.startswith("g") else dict(os.environ, LDCBF_ROLLOUT_G=blk[1:])
+    env = (dict(os.environ, LDCBF_ROLLOUT_G=blk[1:]) if blk.startswith("g") else
+           dict(os.environ, LDCBF_ROLLOUT_START=blk[1:]) if blk.startswith("s") else dict(os.environ, LDCBF_ROLLOUT_BLOCK=blk))
     print(subprocess.run([sys.executable, "-c", CODE], env=env, capture_output=True, text=True).stdout.strip(), flush=True)
