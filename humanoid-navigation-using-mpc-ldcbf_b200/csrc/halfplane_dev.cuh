@@ -39,15 +39,23 @@ constexpr double KEY_NONE = 1.0e300;      // "no edge yet": finite so that the t
 
 // Closest point of segment AB to P.  Returns the squared distance d2 (EXACT: dot2 in the reference's operation
 // order, compared through key_less), writes c; `cross` is incremented when the edge A->B toggles the crossing parity.
+// np.power(np.linalg.norm(AB), 2) of an edge: a property of the map, not of the query point
+__device__ __forceinline__ double edge_den_exact(double2 A, double2 Bv) {
+    const double abx = __dsub_rn(Bv.x, A.x), aby = __dsub_rn(Bv.y, A.y);
+    const double nrm = __dsqrt_rn(dot2(abx, aby, abx, aby));
+    return __dmul_rn(nrm, nrm);
+}
+
+// den_pre: the edge's edge_den_exact() computed earlier (the closed-loop kernel tabulates it once per run: the square
+// root and the product are then off the per-step critical path, same bits), or a negative value to compute it here.
 template <bool EXACT>
 __device__ __forceinline__ double edge_closest(double px, double py, double2 A, double2 Bv, double& cx, double& cy,
-                                               int& cross) {
+                                               int& cross, double den_pre = -1.0) {
     const bool f0 = A.y >= py, f1 = Bv.y >= py;
     if (EXACT) {
         const double apx = __dsub_rn(px, A.x), apy = __dsub_rn(py, A.y);
         const double abx = __dsub_rn(Bv.x, A.x), aby = __dsub_rn(Bv.y, A.y);
-        const double nrm = __dsqrt_rn(dot2(abx, aby, abx, aby));
-        const double den = __dmul_rn(nrm, nrm);                          // np.power(np.linalg.norm(AB), 2)
+        const double den = den_pre >= 0.0 ? den_pre : edge_den_exact(A, Bv);   // np.power(np.linalg.norm(AB), 2)
         double t = __ddiv_rn(dot2(apx, apy, abx, aby), den);
         t = (t != t) ? 1.0 : fmax(0.0, fmin(1.0, t));                    // max(0, min(1, t)); NaN -> 1
         cx = __dadd_rn(A.x, __dmul_rn(t, abx));
@@ -115,16 +123,18 @@ __device__ __forceinline__ double4 halfplane_serial(double px, double py, const 
 // G lanes share a ring: lane l takes edges l, l + G, ..., an xor butterfly merges the partial results by the rule of
 // halfplane_split_kernel (order by the rounded distance, ties towards the lower edge index = the first strict minimum
 // of the serial walk; crossing counts are summed).  Every lane returns the same (c, eta), bit-equal to the serial walk.
-template <bool EXACT, int G>
+// LDG = false: `ring` may point to shared memory (the closed-loop kernel stages the scenario's map there): plain loads.
+template <bool EXACT, int G, bool LDG = true>
 __device__ __forceinline__ double4 halfplane_group(double px, double py, const double2* ring, int V, int lane,
-                                                   unsigned gmask) {
-    if (G == 1) return halfplane_serial<EXACT>(px, py, ring, V);
+                                                   unsigned gmask, const double* den = nullptr) {
+    if (G == 1 && !den) return halfplane_serial<EXACT>(px, py, ring, V);
     double best = KEY_NONE, bcx = 0.0, bcy = 0.0;
     int be = 0x7fffffff, cross = 0;
     for (int e = lane; e < V; e += G) {
-        const double2 A = __ldg(ring + e), Bv = __ldg(ring + ((e + 1 == V) ? 0 : e + 1));
+        const int e1 = (e + 1 == V) ? 0 : e + 1;
+        const double2 A = LDG ? __ldg(ring + e) : ring[e], Bv = LDG ? __ldg(ring + e1) : ring[e1];
         double cx, cy;
-        const double key = edge_closest<EXACT>(px, py, A, Bv, cx, cy, cross);
+        const double key = edge_closest<EXACT>(px, py, A, Bv, cx, cy, cross, (EXACT && den) ? den[e] : -1.0);
         if (key_less<EXACT>(key, best)) { best = key; bcx = cx; bcy = cy; be = e; }
     }
 #pragma unroll

@@ -770,12 +770,23 @@ LDCBF_HD void qp_warm_start(const StepConst& C, const int (&codes)[2 * N], doubl
 
 // Row codes of the final active set, shifted by one stage for the next MPC step (stage k of this step is stage k-1 of
 // the next one; rows of the first stage disappear).  out[j] = -1 where nothing carries over.
+// dup_last: the rows that were active at the LAST stage are also guessed active at the new last stage (which otherwise
+// starts without rows), as far as free entries remain: a walking gait is close to periodic over one stage.
 template <int N, int MO, int WS>
-LDCBF_HD void shift_codes(const QpState<N, MO>& s, const double* ws, int (&out)[2 * N]) {
+LDCBF_HD void shift_codes(const QpState<N, MO>& s, const double* ws, int (&out)[2 * N], bool dup_last = false) {
     constexpr int NV = 2 * N;
+    int extra[NV];
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         int code = ((s.amask >> j) & 1u) ? (int)RC(j) : -1;
+        extra[j] = -1;
+        if (dup_last && code >= 0) {
+            const int id = code >> 1;
+            const bool last = id < 2 * N ? id >= 2 * (N - 1)
+                            : id < 4 * N ? id - 2 * N >= 2 * (N - 1)
+                            : id < 4 * N + N * MO ? id - 4 * N >= (N - 1) * MO : false;
+            if (last) extra[j] = code;
+        }
         if (code >= 0) {
             const int id = code >> 1, side = code & 1;
             int nid = -1;
@@ -785,6 +796,16 @@ LDCBF_HD void shift_codes(const QpState<N, MO>& s, const double* ws, int (&out)[
             code = nid >= 0 ? 2 * nid + side : -1;
         }
         out[j] = code;
+    }
+    if (dup_last) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            bool pending = extra[j] >= 0;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                if (pending && out[i] < 0) { out[i] = extra[j]; pending = false; }
+            }
+        }
     }
 }
 

@@ -35,7 +35,8 @@ struct RolloutIO {
     // ABI 2: half-planes of the obstacles beyond the MO register-resident ones ([B,max_obs] double4, library-owned
     // scratch), iteration counter, per-scenario reason the loop ended (LDCBF_END_*)
     double4* ce_scratch; unsigned long long* total_iters; int32_t* end_code;
-    int start_mode;   // development switch LDCBF_ROLLOUT_START: 0 shifted active set (default), 1 geometric guess every step
+    int start_mode;   // LDCBF_ROLLOUT_START: 2 shifted active set + last stage repeated (default), 0 shifted only, 1 geometric guess
+    double* den_scratch;   // [B,max_obs,max_verts] edge constants of the EXACT ring walk, tabulated once per run
 };
 
 // G lanes per scenario (small batches): the kernel time is the slowest scenario's chain of sequential steps, and a
@@ -45,8 +46,9 @@ struct RolloutIO {
 // that fill the GPU.
 template <int N, int MO, bool EXACT, int BLOCK, int G>
 __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int T, int n_goals, int max_steps_per_goal,
-                                                      int substeps, int max_obs, int max_verts, RolloutIO io) {
-    extern __shared__ double qp_ws[];
+                                                      int substeps, int max_obs, int max_verts, int map_doubles,
+                                                      RolloutIO io) {
+    extern __shared__ __align__(32) double qp_ws[];
     const int b = (blockIdx.x * BLOCK + threadIdx.x) / G;
     if (b >= B) return;                                       // whole groups leave together (G divides BLOCK)
     const int glane = threadIdx.x % G;
@@ -57,8 +59,35 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
     const bool right_first = io.right_first[b] != 0;
     const int nt = min(io.nobs[b], max_obs);
     const int nb = min(nt, MO);
-    double4* ces = io.ce_scratch + (size_t)b * max_obs;     // half-planes of this step; obstacles MO.. are streamed from here
     const int n_stream = nt - nb;
+    // The scenario's map for the whole run — vertex rings, the edge constants of the bit-exact ring walk (|AB|^2 as the
+    // reference forms it, a square root and a product: tabulated once, off the per-step critical path, same bits), the
+    // vertex counts and the half-planes of the current step — lives in SHARED memory when it fits (map_doubles > 0: the
+    // launcher reserved map_doubles doubles per scenario behind the solver workspaces): no global load is left in the
+    // step loop (clock64 profile: the ring walk was the largest phase of a step, 12 k of ~32 k cycles, most of it
+    // waiting for L2).  Otherwise the same pointers refer to global memory (vertices in place, scratch from the pool).
+    double4* ces;
+    const double2* rings;
+    double* dens;
+    const int32_t* nvs;
+    if (map_doubles > 0) {
+        double* m = qp_ws + (size_t)QpWorkspace<N>::DOUBLES * BLOCK + (size_t)(threadIdx.x / G) * map_doubles;
+        ces = reinterpret_cast<double4*>(m);
+        double2* sv = reinterpret_cast<double2*>(m + 4 * max_obs);
+        dens = m + 4 * max_obs + 2 * max_obs * max_verts;
+        int32_t* snv = reinterpret_cast<int32_t*>(dens + max_obs * max_verts);
+        const double2* gv = io.verts + (size_t)b * max_obs * max_verts;
+        for (int i = glane; i < nt * max_verts; i += G) sv[i] = gv[i];
+        for (int o = glane; o < max_obs; o += G) snv[o] = o < nt ? min(io.nverts[(size_t)b * max_obs + o], max_verts) : 0;
+        __syncwarp(gmask);
+        rings = sv; nvs = snv;
+    } else {
+        ces = io.ce_scratch + (size_t)b * max_obs;
+        rings = io.verts + (size_t)b * max_obs * max_verts;
+        dens = (EXACT && io.den_scratch) ? io.den_scratch + (size_t)b * max_obs * max_verts : nullptr;
+        nvs = io.nverts + (size_t)b * max_obs;
+    }
+    if (!EXACT) dens = nullptr;
     const double dl = io.delta ? io.delta[b] : 0.0;
     const Limits lim = load_limits(C, io.limits, (size_t)b);
     double* tX = (io.traj_X && writer) ? io.traj_X + (size_t)b * (T + 1) * 5 : nullptr;
@@ -68,6 +97,14 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
 #if defined(LDCBF_ROLLOUT_PROFILE) && defined(__CUDA_ARCH__)
     long long prof_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, prof_t_ = clock64();
 #endif
+    // lane l of the group tabulates the constants of the edges it will walk, so every lane later reads its own stores
+    if (dens) {
+        for (int o = 0; o < nt; ++o) {
+            const int V = min(nvs[o], max_verts);
+            const double2* ring = rings + (size_t)o * max_verts;
+            for (int e = glane; e < V; e += G) dens[(size_t)o * max_verts + e] = edge_den_exact(ring[e], ring[(e + 1 == V) ? 0 : e + 1]);
+        }
+    }
     int gi = 0, kstep = 0, total = 0, solves = 0, iters_sum = 0, last_status = LDCBF_STATUS_SOLVED;
     int end_code = LDCBF_END_BUDGET;
     int warm[2 * N];                       // active set of the previous step, shifted by one stage (-1: none)
@@ -107,9 +144,9 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
             // stores the same value and reads back its own store
 #pragma unroll 1
             for (int o = 0; o < nt; ++o) {
-                const int V = min(io.nverts[(size_t)b * max_obs + o], max_verts);
-                ces[o] = V > 0 ? halfplane_group<EXACT, G>(px, py, io.verts + ((size_t)b * max_obs + o) * max_verts, V,
-                                                           glane, gmask)
+                const int V = min(nvs[o], max_verts);
+                ces[o] = V > 0 ? halfplane_group<EXACT, G, false>(px, py, rings + (size_t)o * max_verts, V, glane, gmask,
+                                                                  dens ? dens + (size_t)o * max_verts : nullptr)
                                : make_double4(0.0, 0.0, 0.0, 0.0);
             }
             double4 ce[MO];
@@ -137,7 +174,7 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
                 while (!qs.done) qp_trip<N, MO, BLOCK>(C, ws, qs);
                 RO_T(4);
                 qp_finish<N, MO>(C, qs, S);
-                shift_codes<N, MO, BLOCK>(qs, ws, warm);
+                shift_codes<N, MO, BLOCK>(qs, ws, warm, io.start_mode == 2);
                 RO_T(5);
             }
             solves += writer ? 1 : 0;
@@ -201,13 +238,20 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
 template <int N, int MO, bool EXACT, int BLOCK, int G = 1>
 static int launch_rollout_block(const StepConst& C, int B, int T, int n_goals, int msg, int sub, int max_obs,
                                 int max_verts, const RolloutIO& io, cudaStream_t st) {
-    const size_t smem = (size_t)QpWorkspace<N>::DOUBLES * sizeof(double) * BLOCK;
+    size_t smem = (size_t)QpWorkspace<N>::DOUBLES * sizeof(double) * BLOCK;
+    // per scenario: half-planes (4 per obstacle), vertices (2 per vertex), edge constants (1 per vertex), vertex counts;
+    // rounded to 32 B; staged when the block's share stays below 96 KB (several blocks per SM), else read from global
+    int map_doubles = 4 * max_obs + 3 * max_obs * max_verts + (max_obs + 1) / 2;
+    map_doubles = (map_doubles + 3) / 4 * 4;
+    const size_t map_bytes = (size_t)map_doubles * sizeof(double) * (BLOCK / G);
+    if (smem + map_bytes <= 96 * 1024) smem += map_bytes; else map_doubles = 0;
     auto kern = rollout_kernel<N, MO, EXACT, BLOCK, G>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_last_error(e); return LDCBF_E_LAUNCH; }
     }
-    kern<<<(unsigned)(((size_t)B * G + BLOCK - 1) / BLOCK), BLOCK, smem, st>>>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io);
+    kern<<<(unsigned)(((size_t)B * G + BLOCK - 1) / BLOCK), BLOCK, smem, st>>>(C, B, T, n_goals, msg, sub, max_obs, max_verts,
+                                                                              map_doubles, io);
     return check_launch();
 }
 
@@ -269,18 +313,21 @@ extern "C" int ldcbf_rollout_f64(const ldcbf_params* prm, int B, int N, int T, i
     // obstacle): up to 8 are then held in registers, further ones (the reference's CROWDED maps have 20,
     // simulation_1.py:201-231) are streamed from it during the scans
     double4* scratch = nullptr;
+    const bool exact = (prm->flags & LDCBF_FLAG_FAST_GEOMETRY) == 0;
+    const size_t ce_bytes = sizeof(double4) * (size_t)B * max_obs;
+    const size_t den_bytes = exact ? sizeof(double) * (size_t)B * max_obs * max_verts : 0;   // edge constants, exact mode
     {
         cudaMemPool_t pool = workspace_pool();
-        cudaError_t e = pool ? cudaMallocFromPoolAsync(&scratch, sizeof(double4) * (size_t)B * max_obs, pool, st)
-                             : cudaErrorMemoryAllocation;
+        cudaError_t e = pool ? cudaMallocFromPoolAsync(&scratch, ce_bytes + den_bytes, pool, st) : cudaErrorMemoryAllocation;
         if (e != cudaSuccess) { set_last_error(e); cudaGetLastError(); return LDCBF_E_LAUNCH; }
     }
+    double* den_table = exact ? reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + ce_bytes) : nullptr;
     const RolloutIO io{state, goals, right_first, reinterpret_cast<const double2*>(verts), nverts, nobs, delta, limits,
                        traj_X, traj_U, steps, goal_steps, status,
                        reinterpret_cast<unsigned long long*>(total_solves),
                        (prm->flags & LDCBF_FLAG_FAST_GEOMETRY) != 0, (prm->flags & LDCBF_FLAG_COLD_START) == 0,
                        scratch, reinterpret_cast<unsigned long long*>(total_iters), end_code,
-                       getenv("LDCBF_ROLLOUT_START") ? atoi(getenv("LDCBF_ROLLOUT_START")) : 0};
+                       getenv("LDCBF_ROLLOUT_START") ? atoi(getenv("LDCBF_ROLLOUT_START")) : 2, den_table};
     int rc;
     switch (N) {
         case 1: rc = dispatch_rollout<1>(C, B, T, n_goals, max_steps_per_goal, sub, max_obs, max_verts, io, st); break;
