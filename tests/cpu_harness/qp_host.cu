@@ -215,3 +215,31 @@ extern "C" int qp_host_solve_n3_pref(const ldcbf_params* prm, int B, int max_obs
     }
     return 0;
 }
+
+// Analysis aid: the kernel's geometric guess and the FINAL active set (row codes 2*id + side, -1 = empty slot) of one
+// open-loop solve, to study how far the guess is from the optimum's active set.
+extern "C" int qp_host_active_sets_n3(const ldcbf_params* prm, const double* x0, double theta0, const double* goal,
+                                      const int8_t* foot, const double* c_eta, int nobs_b, double delta,
+                                      const int* codes_in, int* guess_out, int* final_out, int32_t* status, int32_t* iters) {
+    using namespace ldcbf;
+    constexpr int N = 3, MO = 4;
+    const StepConst C = make_const(*prm);
+    int ft[N + 1];
+    for (int k = 0; k <= N; ++k) ft[k] = foot[k];
+    double4 ce[MO];
+    const int nb = nobs_b < MO ? nobs_b : MO;
+    for (int o = 0; o < MO; ++o) ce[o] = (o < nb) ? make_double4(c_eta[4 * o], c_eta[4 * o + 1], c_eta[4 * o + 2], c_eta[4 * o + 3]) : make_double4(0, 0, 0, 0);
+    double ws[QpWorkspace<N>::DOUBLES];
+    QpState<N, MO> s;
+    qp_setup<N, MO, 1>(C, x0[0], x0[1], x0[2], x0[3], theta0, goal[0], goal[1], ft, ce, nb, nullptr, 0, delta,
+                       load_limits(C, nullptr, 0), ws, s);
+    int codes[2 * N];
+    for (int j = 0; j < 2 * N; ++j) codes[j] = codes_in[j];
+    if (codes_in[0] == -2) guess_codes<N, MO>(s, codes);
+    for (int j = 0; j < 2 * N; ++j) guess_out[j] = codes[j];
+    qp_warm_start<N, MO, 1>(C, codes, ws, s);
+    while (!s.done) qp_trip<N, MO, 1>(C, ws, s);
+    for (int j = 0; j < 2 * N; ++j) final_out[j] = ((s.amask >> j) & 1u) ? (int)ws[2 * (2 * N) * (2 * N) + j] : -1;
+    *status = s.status; *iters = s.iters;
+    return 0;
+}
