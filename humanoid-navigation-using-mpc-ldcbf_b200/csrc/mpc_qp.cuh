@@ -33,6 +33,9 @@ namespace ldcbf {
 // The solver source also compiles for the host (tests/cpu_harness builds it into a test-only library so the
 // algorithm is exercised by the CPU test suite); the product library only ever launches it on the device.
 #define LDCBF_HD __host__ __device__ __forceinline__
+#if defined(LDCBF_HOST_COUNTERS)
+static long long ldcbf_host_dependent_guesses = 0;      // analysis aid of the host build (tests/cpu_harness)
+#endif
 LDCBF_HD double add_rn(double a, double b) {
 #ifdef __CUDA_ARCH__
     return __dadd_rn(a, b);
@@ -602,9 +605,11 @@ LDCBF_HD void guess_codes(const QpState<N, MO>& s, int (&codes)[2 * N]) {
 // again (at most NV rounds), w = g + N u.  A guess that turns out dependent falls back to the cold start.  The
 // result is exact whatever the guess; a good guess replaces ~15 trips by 2-4.
 // codes[j] = 2*id + (upper side) or -1.  Must be called right after qp_setup (w = g, empty active set).
-// ROLLED: the loop that decodes the guessed rows is not unrolled — one copy in the instruction stream, for the
-// closed-loop kernel that is bound by instruction fetch; the open-loop kernels keep the unrolled form (the race kernel
-// is bound by the latency of one warp's dependent chain: 60 -> 79 us at B = 4096 with the rolled loop).
+// ROLLED (the closed-loop kernel): the loop that decodes the guessed rows is not unrolled — one copy in the instruction
+// stream, that kernel is bound by instruction fetch; the open-loop kernels keep the unrolled form (the race kernel is
+// bound by the latency of one warp's dependent chain: 60 -> 79 us at B = 4096 with the rolled loop) — and a guessed row
+// that depends on the rows before it is taken out individually (see the rounds below); the open-loop guess, velocity
+// rows only, cannot be dependent and keeps the plain test.
 template <int N, int MO, int WS, bool ROLLED = false>
 LDCBF_HD void qp_warm_start(const StepConst& C, const int (&codes)[2 * N], double* ws, QpState<N, MO>& s) {
     constexpr int NV = 2 * N;
@@ -696,25 +701,40 @@ LDCBF_HD void qp_warm_start(const StepConst& C, const int (&codes)[2 * N], doubl
         ++s.iters;      // a round costs about one trip (Cholesky, two solves) and is counted as one
         // Cholesky, u = G^-1 rhs
         double L[NV][NV];
-        bool indep = true;      // every pivot above 1e-10 of its diagonal entry (compared without the division)
+        // A guessed row whose pivot falls below 1e-10 of its diagonal entry (compared without the division) depends on
+        // the rows before it: it is taken out on the spot — its row and column of the factor become the identity, which
+        // is exactly the factor of the Gram matrix without that row — instead of giving up the whole guess (5 % of the
+        // closed-loop steps had such a row, each then cost a cold start of ~25 trips: the p99 of the trips per step).
+        unsigned dep = 0;
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             double dj = GM(j, j);
             const double diag = dj;
 #pragma unroll
             for (int l = 0; l < j; ++l) dj -= L[j][l] * L[j][l];
-            indep = indep && dj > 1e-10 * diag;
-            const double inv = rsqrt_f64(fmax(dj, 1e-300));
+            const bool bad = ((mask >> j) & 1u) && !(dj > 1e-10 * diag);
+            dep |= bad ? (1u << j) : 0u;
+            if (!ROLLED && bad) fail = true;        // open-loop guesses (velocity rows only) are independent by construction
+            const double inv = (ROLLED && bad) ? 1.0 : rsqrt_f64(fmax(dj, 1e-300));
             L[j][j] = inv;
 #pragma unroll
             for (int i = j + 1; i < NV; ++i) {
                 double v = GM(i, j);
 #pragma unroll
                 for (int l = 0; l < j; ++l) v -= L[i][l] * L[j][l];
-                L[i][j] = v * inv;
+                L[i][j] = (ROLLED && bad) ? 0.0 : v * inv;
+            }
+            if (ROLLED) {
+#pragma unroll
+                for (int l = 0; l < j; ++l) L[j][l] = bad ? 0.0 : L[j][l];
             }
         }
-        if (!indep) { fail = true; break; }                     // dependent guess
+        if (!ROLLED && fail) break;                 // dependent guess: back to the cold start
+        if (!ROLLED) dep = 0;
+        mask &= ~dep;
+#if !defined(__CUDA_ARCH__) && defined(LDCBF_HOST_COUNTERS)
+        if (dep) ++ldcbf_host_dependent_guesses;
+#endif
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             double v = ((mask >> j) & 1u) ? rhs[j] : 0.0;
@@ -732,19 +752,19 @@ LDCBF_HD void qp_warm_start(const StepConst& C, const int (&codes)[2 * N], doubl
         unsigned neg = 0;
 #pragma unroll
         for (int j = 0; j < NV; ++j) if (((mask >> j) & 1u) && !(uu[j] >= 0.0)) neg |= 1u << j;
-        if (neg == 0u) break;
-        if (round == NV) { fail = true; break; }
+        if (round == NV && neg != 0u) { fail = true; break; }
         mask &= ~neg;                                           // drop the rows with negative multipliers
+        const unsigned gone = neg | dep;                        // ... and clear them and the dependent ones from the workspace
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
-            if ((neg >> j) & 1u) {
+            if ((gone >> j) & 1u) {
 #pragma unroll
                 for (int i = 0; i < NV; ++i) { AN(j, i) = 0.0; GM(j, i) = 0.0; GM(i, j) = 0.0; }
                 GM(j, j) = 1.0;
                 RC(j) = -1.0;
             }
         }
-        if (mask == 0u) break;
+        if (neg == 0u || mask == 0u) break;
     }
     if (fail || mask == 0u) {                                   // back to the cold start
 #pragma unroll

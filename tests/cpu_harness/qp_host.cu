@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE: compiles the solver source of the CUDA kernels (csrc/mpc_qp.cuh) for the HOST so that the
 // CPU test suite can run the exact same algorithm code without a GPU.  Never linked into libldcbf_b200.so.
+#define LDCBF_HOST_COUNTERS
 #include "mpc_qp.cuh"
 
 namespace ldcbf { void set_last_error(cudaError_t) {} }
@@ -24,11 +25,11 @@ extern "C" int qp_host_solve_n3_warm(const ldcbf_params* prm, int max_obs, const
     int codes[2 * N];
     for (int j = 0; j < 2 * N; ++j) codes[j] = codes_in[j];
     if (codes_in[0] == -2) guess_codes<N, MO>(s, codes);      // -2: the kernel's own initial guess
-    qp_warm_start<N, MO, 1>(C, codes, ws, s);
+    qp_warm_start<N, MO, 1, true>(C, codes, ws, s);      // the closed-loop kernel's instantiation
     while (!s.done) qp_trip<N, MO, 1>(C, ws, s);
     QpSolution<N> S;
     qp_finish<N, MO>(C, s, S);
-    shift_codes<N, MO, 1>(s, ws, codes);
+    shift_codes<N, MO, 1>(s, ws, codes, (prm->flags & 0x100) != 0);      // test-only bit: repeat the last stage's rows
     for (int j = 0; j < 2 * N; ++j) codes_out[j] = codes[j];
     for (int k = 0; k < N; ++k) { U[2 * k] = S.ux[k]; U[2 * k + 1] = S.uy[k]; }
     for (int k = 0; k <= N; ++k) { X[4 * k] = S.px[k]; X[4 * k + 1] = S.vx[k]; X[4 * k + 2] = S.py[k]; X[4 * k + 3] = S.vy[k]; }
@@ -243,3 +244,5 @@ extern "C" int qp_host_active_sets_n3(const ldcbf_params* prm, const double* x0,
     *status = s.status; *iters = s.iters;
     return 0;
 }
+
+extern "C" long long qp_host_dependent_guesses(void) { return ldcbf::ldcbf_host_dependent_guesses; }
