@@ -258,21 +258,26 @@ static int launch_rollout_block(const StepConst& C, int B, int T, int n_goals, i
 template <int N, int MO>
 static int launch_rollout(const StepConst& C, int B, int T, int n_goals, int msg, int sub, int max_obs, int max_verts,
                           const RolloutIO& io, cudaStream_t st) {
-    // 32-lane warps also for small batches: 8-lane blocks (as in the step kernels) were measured — no change at
-    // B = 4096 (5.4 ms: the kernel time is the slowest scenario's 150 sequential steps), 18 -> 22 ms at B = 8192
-    // the GPU has idle lanes: 4 per scenario, 8 scenarios per warp.  Measured at B = 4096 (config 2, warm / cold):
-    // 1 lane 5.42 / 6.28 ms, 4 lanes 5.01 / 5.45 ms, 8 lanes 7.35 / 6.00 ms (eight times the warps of this large kernel
-    // at different places in its code: the time then goes to instruction fetch).
-    if (B < 148 * 4 * 16 && max_verts > 8) {
+    // Lanes per scenario for the ring walk (the solve is then run redundantly by the lanes of a group).  The kernel is a
+    // chain of dependent steps per scenario, so more lanes shorten the ring walk — until the warps get in each other's
+    // way: every warp streams ~100 KB of code per step, and beyond ~2 warps per SM instruction fetch dominates (DESIGN.md
+    // §6).  Measured after the warm-start changes of round 2 (ms per config-2 pass, lanes per scenario 1 / 2 / 4):
+    // B = 2048: - / 4.73 / 4.04;  3072: - / 4.79 / 4.89;  4096: 6.38 / 5.00 / 6.07;  6144: 6.39 / 5.80 / -;
+    // 8192: 6.46 / 7.26 / -.  Blocks of 16 or 8 threads (more, smaller warps) always lost.
+    if (B < 7168 && max_verts > 8) {
+        static const int rg_env = getenv("LDCBF_ROLLOUT_G") ? atoi(getenv("LDCBF_ROLLOUT_G")) : 0;
         static const int rb = getenv("LDCBF_ROLLOUT_BLOCK") ? atoi(getenv("LDCBF_ROLLOUT_BLOCK")) : 32;
-        static const int rg = getenv("LDCBF_ROLLOUT_G") ? atoi(getenv("LDCBF_ROLLOUT_G")) : 4;
-        if (!io.fast_geometry && rg == 1) return launch_rollout_block<N, MO, true, 32, 1>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
-        if (!io.fast_geometry && rg == 2) return launch_rollout_block<N, MO, true, 32, 2>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
-        if (!io.fast_geometry && rg == 8) return launch_rollout_block<N, MO, true, 32, 8>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
-        if (!io.fast_geometry && rb == 8) return launch_rollout_block<N, MO, true, 8, 4>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
-        if (!io.fast_geometry && rb == 16) return launch_rollout_block<N, MO, true, 16, 4>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
-        return io.fast_geometry ? launch_rollout_block<N, MO, false, 32, 4>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st)
-                                : launch_rollout_block<N, MO, true, 32, 4>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
+        const int rg = rg_env ? rg_env : (B < 3072 ? 4 : 2);
+        if (io.fast_geometry) {
+            if (rg == 2) return launch_rollout_block<N, MO, false, 32, 2>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
+            return launch_rollout_block<N, MO, false, 32, 4>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
+        }
+        if (rb == 8) return launch_rollout_block<N, MO, true, 8, 4>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
+        if (rb == 16) return launch_rollout_block<N, MO, true, 16, 4>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
+        if (rg == 1) return launch_rollout_block<N, MO, true, 32, 1>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
+        if (rg == 2) return launch_rollout_block<N, MO, true, 32, 2>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
+        if (rg == 8) return launch_rollout_block<N, MO, true, 32, 8>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
+        return launch_rollout_block<N, MO, true, 32, 4>(C, B, T, n_goals, msg, sub, max_obs, max_verts, io, st);
     }
     const bool big = B >= 148 * 4 * 128;
     if (io.fast_geometry)

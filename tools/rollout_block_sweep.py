@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.join(%r, "humanoid-navigation-using-mpc-ldcbf_b200"))
 import numpy as np, torch
 import ldcbf_b200 as L
 from ldcbf_b200 import scenarios
-B = 4096
+B = int(os.environ.get("ROLL_B", "4096"))
 sc = scenarios.config2(B, seed=0)
 eng = L.BatchedHumanoidMPC(sc["goal"], sc["verts"], sc["nverts"], sc["nobs"], N_horizon=3, sampling_time=0.4, delta=np.full(B, 1e-6))
 st0 = torch.as_tensor(sc["state"]).cuda(); rf = torch.as_tensor(sc["right_first"].astype(np.int8)).cuda()
