@@ -447,15 +447,17 @@ def run_ours(args):
         flops = iters_rank * FLOP_PER_ITER + solves_rank * (FLOP_SETUP + FLOP_K1)
         k_ms = statistics.mean(ts)
         ach = flops / (k_ms * 1e-3) / 1e12
-        line["roofline"] = {"bound": "fp64", "kernel": "rollout_kernel<3,4,exact,32,4>", "achieved": ach, "peak": peak_fp64,
+        lanes = 4 if B < 3072 else 2 if B < 7168 else 1             # csrc/rollout.cu: launch_rollout
+        line["roofline"] = {"bound": "fp64", "kernel": f"rollout_kernel<3,4,exact,32,{lanes}>", "achieved": ach, "peak": peak_fp64,
                             "unit": "TFLOP/s", "frac": ach / peak_fp64, "traffic": profile_traffic("rollout"),
                             "kernel_ms": k_ms,
                             "peak_source": "FP64 FMA-chain probe measured in this run (MEASURED_PEAKS.json has no fp64 "
                                            "entry); profiles/ holds the probe's own ncu counters",
                             "flop_model": f"iterations*{FLOP_PER_ITER:.0f} + solves*({FLOP_SETUP:.0f} + {FLOP_K1:.0f} for the "
                                           "52 ring edges) (DESIGN.md §6)",
-                            "note": "4096 closed loops are 4096 sequential chains of <= 150 dependent solves: 512 warps on "
-                                    "592 SM sub-partitions, bound by the instruction latency of the longest chain; "
+                            "note": "4096 closed loops are 4096 sequential chains of <= 150 dependent solves: 256 warps on "
+                                    "592 SM sub-partitions, bound by the instruction latency of the longest chain (ncu: "
+                                    "4.1 cycles per issued instruction, 2.0 of them fixed-latency dependencies); "
                                     "large_batch shows the same solver with the GPU full"}
         # kernel-only timing of the open-loop solve for step0's roofline (same inputs, L2 flushed)
         t_qp = timed_steps(lambda: L.mpc_qp(prm, d["x0"], d["th"], d["goal"], d["foot"], out["c_eta"], d["nobs"],
