@@ -233,3 +233,19 @@ def test_large_batch_split_other_shapes(L):
     assert np.abs(a["obj"][ok] - c["obj"][ok]).max() <= 1e-6 * np.abs(c["obj"][ok]).max()
     assert np.all(np.isnan(a["U"][~ok]))
     assert L.lib().ldcbf_trim_workspace() == 0
+
+
+def test_marginally_feasible_states_on_the_gpu():
+    """tests/golden/marginal_feasible_states.npz through ldcbf_mpc_qp_f64 (see test_solver_host_build.py): solved, equal to
+    the oracle's optimum, in the one-thread, racing and large-batch launch shapes."""
+    import os
+    import ldcbf_b200 as L
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "marginal_feasible_states.npz"))["rows"]
+    cu = lambda a, dt=torch.float64: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).cuda()
+    for rep in (1, 1024, 13000):                       # racing kernel, racing kernel (wider blocks), one thread per scenario
+        rows = np.tile(g, (rep, 1))
+        out = L.mpc_qp(L.default_params(0.4), cu(rows[:, :4]), cu(rows[:, 4]), cu(rows[:, 5:7]), cu(rows[:, 7:11], torch.int8),
+                       cu(rows[:, 11:23].reshape(-1, 3, 4)), cu(np.full(len(rows), 3), torch.int32), delta=cu(np.full(len(rows), 1e-6)))
+        st, U = out["status"].cpu().numpy(), out["U"].cpu().numpy()
+        assert (st == 0).all()
+        assert np.abs(U - rows[:, 23:29].reshape(-1, 3, 2)).max() <= 1e-9

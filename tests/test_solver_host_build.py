@@ -229,3 +229,36 @@ def test_host_build_warm_start_is_exact_and_cheaper(host_lib):
     assert steps > 200
     print(f"trips per step: cold {cold_trips / steps:.2f}  warm {warm_trips / steps:.2f}")
     assert warm_trips < 0.6 * cold_trips
+
+
+def test_marginally_feasible_states_are_solved_not_reported_infeasible(host_lib):
+    """States found in closed loops of the bench batch (tests/golden/marginal_feasible_states.npz) where kinematic rows meet as
+    equalities: the feasible set is a point to rounding, the oracle's optimum violates a row by ~1e-11.  With the strict
+    verdict (eps_infeasible = 0) Goldfarb-Idnani proves that row inconsistent and reports infeasible; with the default
+    1e-9 the solve restarts relaxed and returns the oracle's optimum."""
+    import ldcbf_b200
+    from ldcbf_b200.binding import LdcbfParams
+    g = np.load(os.path.join(ROOT, "tests", "golden", "marginal_feasible_states.npz"))["rows"]
+    assert len(g) >= 10
+    for row in g:
+        st, goal, foot, ce, U_ref = row[:5], row[5:7], row[7:11].astype(np.int8), row[11:23].reshape(1, 3, 4), row[23:29].reshape(3, 2)
+        out = host_solve(host_lib, st[None], goal[None], foot[None], ce, np.array([3]), np.array([1e-6]))
+        assert out["status"][0] == 0
+        assert np.abs(out["U"][0] - U_ref).max() <= 1e-9
+        assert abs(out["obj"][0] - row[29]) <= 1e-9 * abs(row[29])
+    # the strict verdict on the same states
+    prm = LdcbfParams()
+    ldcbf_b200.lib().ldcbf_params_default(ctypes.byref(prm))
+    prm.sampling_time, prm.eps_infeasible = 0.4, 0.0
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    strict = 0
+    for row in g:
+        x0, th, goal = np.ascontiguousarray(row[None, :4]), np.ascontiguousarray(row[4:5]), np.ascontiguousarray(row[None, 5:7])
+        ft, ce = np.ascontiguousarray(row[None, 7:11].astype(np.int8)), np.ascontiguousarray(row[11:23].reshape(1, 3, 4))
+        no, dl = np.array([3], np.int32), np.array([1e-6])
+        o = dict(U=np.zeros((1, 3, 2)), X=np.zeros((1, 4, 4)), theta=np.zeros((1, 4)), omega=np.zeros((1, 3)), obj=np.zeros(1),
+                 status=np.zeros(1, np.int32), iters=np.zeros(1, np.int32))
+        assert host_lib.qp_host_solve_n3(ctypes.byref(prm), 1, 3, P(x0), P(th), P(goal), P(ft), P(ce), P(no), P(dl), P(o["U"]),
+                                         P(o["X"]), P(o["theta"]), P(o["omega"]), P(o["obj"]), P(o["status"]), P(o["iters"])) == 0
+        strict += int(o["status"][0] == 2)
+    assert strict >= len(g) // 2          # found with a warm start in closed loop; most are infeasible from the guess too
