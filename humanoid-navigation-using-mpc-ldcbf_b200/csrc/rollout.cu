@@ -9,9 +9,11 @@
 // and the sub-goal sequencing of MPC/HumanoidMPCVariants/HumanoidMPCWithRRT.py:153-181 (a fresh run per
 // sub-goal: objective memory and foot parity restart, the state carries over).
 //
-// Mapping: one thread per scenario, persistent over all its steps: no per-step launch latency, the
-// scenario's vertex rings stay in L1/L2 (832 B at the basic shape), state and active data in registers.
-// Scenarios are independent, so a block never synchronises.
+// Mapping: one thread (or a group of 2 / 4 lanes that split the ring walk) per scenario, persistent over all its
+// steps: no per-step launch latency; the scenario's map (vertex rings, edge constants, half-planes of the step) is
+// staged in shared memory for the whole run when it fits, state and active data live in registers.  Scenarios are
+// independent, so a block never synchronises.  Every solve is warm-started from the previous step's active set, shifted
+// by one stage and with the last stage repeated (mpc_qp.cuh: shift_codes, qp_warm_start).
 #include <cstdio>
 #include <cstdlib>
 
@@ -39,11 +41,11 @@ struct RolloutIO {
     double* den_scratch;   // [B,max_obs,max_verts] edge constants of the EXACT ring walk, tabulated once per run
 };
 
-// G lanes per scenario (small batches): the kernel time is the slowest scenario's chain of sequential steps, and a
-// third of a step is the serial walk over the scenario's rings (52 edges, each a division and a square root).  The G
-// lanes split every ring (halfplane_group, bit-equal to the serial walk) and then all run the same solve in lockstep
-// (same data, same control flow: no divergence, no communication); lane 0 of the group writes.  G = 1 for batches
-// that fill the GPU.
+// G lanes per scenario (small batches): the kernel time is the slowest scenario's chain of sequential steps, and the
+// largest fixed part of a step is the walk over the scenario's rings (52 edges, each a division and a square root).  The
+// G lanes split every ring (halfplane_group, bit-equal to the serial walk) and then all run the same solve in lockstep
+// (same data, same control flow: no divergence, no communication); lane 0 of the group writes.  G is chosen by batch
+// size in launch_rollout (4 / 2 / 1: more lanes shorten the walk, more warps cost instruction fetch).
 template <int N, int MO, bool EXACT, int BLOCK, int G>
 __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int T, int n_goals, int max_steps_per_goal,
                                                       int substeps, int max_obs, int max_verts, int map_doubles,
