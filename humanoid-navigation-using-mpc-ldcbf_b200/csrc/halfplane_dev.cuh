@@ -48,10 +48,22 @@ __device__ __forceinline__ double edge_den_exact(double2 A, double2 Bv) {
 
 // den_pre: the edge's edge_den_exact() computed earlier (the closed-loop kernel tabulates it once per run: the square
 // root and the product are then off the per-step critical path, same bits), or a negative value to compute it here.
+// The crossing-parity part of edge_closest alone (same operations, same rounding).
 template <bool EXACT>
+__device__ __forceinline__ void edge_cross(double px, double py, double2 A, double2 Bv, int& cross) {
+    const bool f0 = A.y >= py, f1 = Bv.y >= py;
+    if (f0 != f1) {
+        const bool side = EXACT ? __dmul_rn(__dsub_rn(Bv.y, py), __dsub_rn(A.x, Bv.x)) >=
+                                  __dmul_rn(__dsub_rn(Bv.x, px), __dsub_rn(A.y, Bv.y))
+                                : (Bv.y - py) * (A.x - Bv.x) >= (Bv.x - px) * (A.y - Bv.y);
+        cross += (side == f1);
+    }
+}
+
+template <bool EXACT, bool CROSS = true>
 __device__ __forceinline__ double edge_closest(double px, double py, double2 A, double2 Bv, double& cx, double& cy,
                                                int& cross, double den_pre = -1.0) {
-    const bool f0 = A.y >= py, f1 = Bv.y >= py;
+    const bool f0 = CROSS && A.y >= py, f1 = CROSS && Bv.y >= py;
     if (EXACT) {
         const double apx = __dsub_rn(px, A.x), apy = __dsub_rn(py, A.y);
         const double abx = __dsub_rn(Bv.x, A.x), aby = __dsub_rn(Bv.y, A.y);
@@ -145,6 +157,56 @@ __device__ __forceinline__ double4 halfplane_group(double px, double py, const d
         cross += __shfl_xor_sync(gmask, cross, off, G);
         if (key_less<EXACT>(ok, best) || (!key_less<EXACT>(best, ok) && oe < be)) { best = ok; bcx = ocx; bcy = ocy; be = oe; }
     }
+    return finish_halfplane<EXACT>(px, py, bcx, bcy, cross);
+}
+
+// The ring walk of the closed-loop kernel, with temporal coherence: between two steps the CoM moves a fraction of a
+// metre, so the edge that was closest at the previous step (`prev`, kept by the caller per scenario and obstacle) is
+// evaluated first; its squared distance U bounds the minimum from above, and every other edge whose enclosing disc
+// (midpoint M, radius h = |AB| / 2) is farther than that is skipped without the division / square roots of the exact
+// evaluation:  |P - X| >= |P - M| - h for X on AB, so with m2 = |P - M|^2, h2 = h^2, thr = U (1 + 1e-9):
+//     m2 > h2  and  s = m2 + h2 - thr > 0  and  s^2 > 4 h2 m2 (1 + 1e-6)   =>   (|P - M| - h)^2 > thr   =>   skip.
+// A skipped edge's exact squared distance exceeds U by more than 1e-9 relative (the margins dwarf the 1e-16 rounding of
+// the test itself), so its rounded distance can neither beat nor tie the minimum: the result — the minimal rounded
+// distance, ties to the lowest edge index, the rule the lanes are merged with anyway — is bit-identical to the full walk
+// whatever `prev` is (first step: 0).  The crossing parity still visits every edge (two comparisons, rarely more).
+// Config 2: 52 edges, ~4 exact evaluations per scenario and step instead of 52.
+template <bool EXACT, int G>
+__device__ __forceinline__ double4 halfplane_group_pruned(double px, double py, const double2* ring, int V, int lane,
+                                                          unsigned gmask, const double* den, int& prev) {
+    double best = KEY_NONE, bcx = 0.0, bcy = 0.0;
+    int be = 0x7fffffff, cross = 0;
+    const int e0 = (prev >= 0 && prev < V) ? prev : 0;
+    if (lane == e0 % G) {                               // the owner of the previously closest edge evaluates it exactly
+        const double2 A = ring[e0], Bv = ring[(e0 + 1 == V) ? 0 : e0 + 1];
+        best = edge_closest<EXACT, false>(px, py, A, Bv, bcx, bcy, cross, (EXACT && den) ? den[e0] : -1.0);
+        be = e0;
+    }
+    double U = best;
+    if (G > 1) U = __shfl_sync(gmask, best, e0 % G, G);
+    const double thr = U * (1.0 + 1e-9);
+    for (int e = lane; e < V; e += G) {
+        const double2 A = ring[e], Bv = ring[(e + 1 == V) ? 0 : e + 1];
+        edge_cross<EXACT>(px, py, A, Bv, cross);
+        if (e == e0) continue;
+        const double mx = 0.5 * (A.x + Bv.x) - px, my = 0.5 * (A.y + Bv.y) - py;
+        const double hx = 0.5 * (Bv.x - A.x), hy = 0.5 * (Bv.y - A.y);
+        const double m2 = mx * mx + my * my, h2 = hx * hx + hy * hy;
+        const double s = m2 + h2 - thr;
+        if (m2 > h2 && s > 0.0 && s * s > 4.0 * h2 * m2 * (1.0 + 1e-6)) continue;
+        double cx, cy;
+        const double key = edge_closest<EXACT, false>(px, py, A, Bv, cx, cy, cross, (EXACT && den) ? den[e] : -1.0);
+        if (key_less<EXACT>(key, best) || (!key_less<EXACT>(best, key) && e < be)) { best = key; bcx = cx; bcy = cy; be = e; }
+    }
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) {
+        const double ok = __shfl_xor_sync(gmask, best, off, G);
+        const double ocx = __shfl_xor_sync(gmask, bcx, off, G), ocy = __shfl_xor_sync(gmask, bcy, off, G);
+        const int oe = __shfl_xor_sync(gmask, be, off, G);
+        cross += __shfl_xor_sync(gmask, cross, off, G);
+        if (key_less<EXACT>(ok, best) || (!key_less<EXACT>(best, ok) && oe < be)) { best = ok; bcx = ocx; bcy = ocy; be = oe; }
+    }
+    prev = be;
     return finish_halfplane<EXACT>(px, py, bcx, bcy, cross);
 }
 

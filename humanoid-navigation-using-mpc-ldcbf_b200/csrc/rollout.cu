@@ -37,6 +37,7 @@ struct RolloutIO {
     // ABI 2: half-planes of the obstacles beyond the MO register-resident ones ([B,max_obs] double4, library-owned
     // scratch), iteration counter, per-scenario reason the loop ended (LDCBF_END_*)
     double4* ce_scratch; unsigned long long* total_iters; int32_t* end_code;
+    bool prune;       // LDCBF_ROLLOUT_NOPRUNE=1 switches the pruned ring walk off (A/B runs)
     int start_mode;   // LDCBF_ROLLOUT_START: 2 shifted active set + last stage repeated (default), 0 shifted only, 1 geometric guess
     double* den_scratch;   // [B,max_obs,max_verts] edge constants of the EXACT ring walk, tabulated once per run
 };
@@ -72,15 +73,20 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
     const double2* rings;
     double* dens;
     const int32_t* nvs;
+    int32_t* prevs = nullptr;
     if (map_doubles > 0) {
         double* m = qp_ws + (size_t)QpWorkspace<N>::DOUBLES * BLOCK + (size_t)(threadIdx.x / G) * map_doubles;
         ces = reinterpret_cast<double4*>(m);
         double2* sv = reinterpret_cast<double2*>(m + 4 * max_obs);
         dens = m + 4 * max_obs + 2 * max_obs * max_verts;
         int32_t* snv = reinterpret_cast<int32_t*>(dens + max_obs * max_verts);
+        prevs = io.prune ? snv + max_obs : nullptr;              // closest edge of every obstacle at the previous step
         const double2* gv = io.verts + (size_t)b * max_obs * max_verts;
         for (int i = glane; i < nt * max_verts; i += G) sv[i] = gv[i];
-        for (int o = glane; o < max_obs; o += G) snv[o] = o < nt ? min(io.nverts[(size_t)b * max_obs + o], max_verts) : 0;
+        for (int o = glane; o < max_obs; o += G) {
+            snv[o] = o < nt ? min(io.nverts[(size_t)b * max_obs + o], max_verts) : 0;
+            if (prevs) prevs[o] = 0;
+        }
         __syncwarp(gmask);
         rings = sv; nvs = snv;
     } else {
@@ -147,9 +153,15 @@ __global__ void __launch_bounds__(BLOCK) rollout_kernel(StepConst C, int B, int 
 #pragma unroll 1
             for (int o = 0; o < nt; ++o) {
                 const int V = min(nvs[o], max_verts);
-                ces[o] = V > 0 ? halfplane_group<EXACT, G, false>(px, py, rings + (size_t)o * max_verts, V, glane, gmask,
-                                                                  dens ? dens + (size_t)o * max_verts : nullptr)
-                               : make_double4(0.0, 0.0, 0.0, 0.0);
+                if (V <= 0) { ces[o] = make_double4(0.0, 0.0, 0.0, 0.0); continue; }
+                // staged map: walk with pruning around the previous step's closest edge (every lane of the group computes
+                // the same new index and stores it: equal values); otherwise the plain walk
+                int prev = prevs ? prevs[o] : -1;
+                ces[o] = prevs ? halfplane_group_pruned<EXACT, G>(px, py, rings + (size_t)o * max_verts, V, glane, gmask,
+                                                                  dens ? dens + (size_t)o * max_verts : nullptr, prev)
+                               : halfplane_group<EXACT, G, false>(px, py, rings + (size_t)o * max_verts, V, glane, gmask,
+                                                                  dens ? dens + (size_t)o * max_verts : nullptr);
+                if (prevs) prevs[o] = prev;
             }
             double4 ce[MO];
 #pragma unroll
@@ -243,7 +255,7 @@ static int launch_rollout_block(const StepConst& C, int B, int T, int n_goals, i
     size_t smem = (size_t)QpWorkspace<N>::DOUBLES * sizeof(double) * BLOCK;
     // per scenario: half-planes (4 per obstacle), vertices (2 per vertex), edge constants (1 per vertex), vertex counts;
     // rounded to 32 B; staged when the block's share stays below 96 KB (several blocks per SM), else read from global
-    int map_doubles = 4 * max_obs + 3 * max_obs * max_verts + (max_obs + 1) / 2;
+    int map_doubles = 4 * max_obs + 3 * max_obs * max_verts + max_obs;       // ... and two ints per obstacle
     map_doubles = (map_doubles + 3) / 4 * 4;
     const size_t map_bytes = (size_t)map_doubles * sizeof(double) * (BLOCK / G);
     if (smem + map_bytes <= 96 * 1024) smem += map_bytes; else map_doubles = 0;
@@ -333,7 +345,7 @@ extern "C" int ldcbf_rollout_f64(const ldcbf_params* prm, int B, int N, int T, i
                        traj_X, traj_U, steps, goal_steps, status,
                        reinterpret_cast<unsigned long long*>(total_solves),
                        (prm->flags & LDCBF_FLAG_FAST_GEOMETRY) != 0, (prm->flags & LDCBF_FLAG_COLD_START) == 0,
-                       scratch, reinterpret_cast<unsigned long long*>(total_iters), end_code,
+                       scratch, reinterpret_cast<unsigned long long*>(total_iters), end_code, getenv("LDCBF_ROLLOUT_NOPRUNE") == nullptr,
                        getenv("LDCBF_ROLLOUT_START") ? atoi(getenv("LDCBF_ROLLOUT_START")) : 2, den_table};
     int rc;
     switch (N) {

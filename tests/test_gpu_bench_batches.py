@@ -280,3 +280,40 @@ def test_rollout_is_independent_of_the_lanes_per_scenario(L):
         assert np.array_equal(a[:1024], b, equal_nan=True)
     # and the single-lane path (batches that fill the GPU) on a prefix replicated past its threshold is too expensive
     # here; its ring walk is the same device function with one lane (halfplane_serial), covered by the K1 tests
+
+
+def test_rollout_ring_walk_with_pruning_equals_the_full_walk(L):
+    """The closed-loop kernel skips the exact evaluation of edges that provably cannot be the closest (disc bound around
+    the previous step's closest edge, csrc/halfplane_dev.cuh: halfplane_group_pruned).  The same 96 closed loops with the
+    pruning switched off (LDCBF_ROLLOUT_NOPRUNE, read at every call) must give bit-identical trajectories; and every
+    transition replayed through the batched K1 kernel + K2+K3 gives the same next state to 1e-5 (the two solves start
+    differently — shifted active set vs geometric guess — which moves an ill-conditioned vertex by up to ~1e-6)."""
+    import os
+    from ldcbf_b200 import scenarios
+    B, T = 96, 150
+    sc = scenarios.config2(B, seed=17)
+    eng = L.BatchedHumanoidMPC(sc["goal"], sc["verts"], sc["nverts"], sc["nobs"], N_horizon=3, sampling_time=0.4,
+                               delta=np.full(B, MARGIN))
+    rf = cu(sc["right_first"].astype(np.int8), torch.int8)
+    r = eng.rollout(cu(sc["state"]), rf, T)
+    tX, tU, steps = r["traj_X"].cpu().numpy(), r["traj_U"].cpu().numpy(), r["steps"].cpu().numpy()
+    assert steps.max() >= 100
+    os.environ["LDCBF_ROLLOUT_NOPRUNE"] = "1"
+    try:
+        r0 = eng.rollout(cu(sc["state"]), rf, T)
+    finally:
+        del os.environ["LDCBF_ROLLOUT_NOPRUNE"]
+    assert np.array_equal(tX, r0["traj_X"].cpu().numpy(), equal_nan=True)
+    assert np.array_equal(tU, r0["traj_U"].cpu().numpy(), equal_nan=True)
+    assert np.array_equal(steps, r0["steps"].cpu().numpy())
+    worst = 0.0
+    for k in range(0, int(steps.max()), 3):
+        alive = np.flatnonzero(steps > k)
+        foots = scenarios.foot_window(sc["right_first"][alive], k, 3)
+        o = L.mpc_step(L.default_params(0.4), cu(tX[alive, k, :4]), cu(tX[alive, k, 4]), cu(sc["goal"][alive]),
+                       cu(foots, torch.int8), cu(sc["verts"][alive]), cu(sc["nverts"][alive], torch.int32),
+                       cu(sc["nobs"][alive], torch.int32), delta=cu(np.full(len(alive), MARGIN)))
+        assert int((o["status"] != 0).sum().item()) == 0
+        nxt = np.column_stack((o["X"][:, 1].cpu().numpy(), o["theta"][:, 1].cpu().numpy()))
+        worst = max(worst, np.abs(nxt - tX[alive, k + 1]).max())
+    assert worst <= 1e-5, worst
