@@ -683,20 +683,39 @@ LDCBF_HD void qp_warm_start(const StepConst& C, const int (&codes)[2 * N], doubl
     bool fail = false;
     double uu[NV];
     // Gram matrix of the loaded slots (identity on the empty ones), once: a round that drops rows only has to put the
-    // identity back on their rows and columns, the entries between the rows that stay do not change
+    // identity back on their rows and columns, the entries between the rows that stay do not change.  Only shared
+    // memory and the mask are involved, so the closed-loop kernel (ROLLED) runs it as a real loop: 40 instructions of
+    // code instead of ~500 in a kernel that waits for its own code.
+    if (ROLLED) {
+#pragma unroll 1
+        for (int j = 0; j < NV; ++j) {
+            const bool aj = (mask >> j) & 1u;
+#pragma unroll 1
+            for (int l = 0; l <= j; ++l) {
+                double g2 = 0.0;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-        const bool aj = (mask >> j) & 1u;
+                for (int i = 0; i < NV; ++i) g2 += AN(j, i) * AN(l, i);
+                const bool al = (mask >> l) & 1u;
+                g2 = (aj && al) ? g2 : (j == l ? 1.0 : 0.0);
+                GM(j, l) = g2; GM(l, j) = g2;
+            }
+        }
+    } else {
 #pragma unroll
-        for (int l = 0; l <= j; ++l) {
-            double g2 = 0.0;
+        for (int j = 0; j < NV; ++j) {
+            const bool aj = (mask >> j) & 1u;
 #pragma unroll
-            for (int i = 0; i < NV; ++i) g2 += AN(j, i) * AN(l, i);
-            const bool al = (mask >> l) & 1u;
-            g2 = (aj && al) ? g2 : (j == l ? 1.0 : 0.0);
-            GM(j, l) = g2; GM(l, j) = g2;
+            for (int l = 0; l <= j; ++l) {
+                double g2 = 0.0;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) g2 += AN(j, i) * AN(l, i);
+                const bool al = (mask >> l) & 1u;
+                g2 = (aj && al) ? g2 : (j == l ? 1.0 : 0.0);
+                GM(j, l) = g2; GM(l, j) = g2;
+            }
         }
     }
+#pragma unroll 1
     for (int round = 0; round <= NV; ++round) {
         ++s.iters;      // a round costs about one trip (Cholesky, two solves) and is counted as one
         // Cholesky, u = G^-1 rhs
