@@ -12,17 +12,24 @@
 // slower (0.58 vs 0.39 ms at B = 2^20): the 400 B of shared memory per thread capped the SM at 16 warps, and this
 // kernel needs warps more than it needs coalescing — the bit-exact arithmetic costs ~95 instructions per edge
 // (two square roots, one division), so it sits between the HBM and the FP64-issue rooflines.
+#include <cstdint>
+#include <cstdlib>
 #include "halfplane_dev.cuh"
 
 namespace ldcbf {
 
 constexpr int K1_THREADS = 128;
 
+static bool k1_narrow_loads() {      // LDCBF_K1_NARROW=1: 16-byte loads whatever the alignment (A/B measurements, tests)
+    static const bool v = [] { const char* e = getenv("LDCBF_K1_NARROW"); return e && atoi(e) != 0; }();
+    return v;
+}
+
 // Thread t -> obstacle o = t / Bpad, scenario b = t % Bpad (Bpad = B rounded up to a warp): the 32 lanes of a warp walk
 // the SAME obstacle index of 32 consecutive scenarios.  Rings of one index have similar sizes (config 2: 9 / 19 / 24
 // vertices for o = 0 / 1 / 2), so a warp's lanes finish together; with the natural (b, o) order a warp mixed all
 // sizes and ran at mean/max = 72 % lane occupancy (22 of 32 lanes in ncu).
-template <bool EXACT>
+template <bool EXACT, bool WIDE>
 __global__ void __launch_bounds__(K1_THREADS) halfplane_kernel(int B, int Bpad, int max_obs, int max_verts,
                                                                const double* __restrict__ pos, int pos_stride,
                                                                int y_off, const double2* __restrict__ verts,
@@ -36,7 +43,8 @@ __global__ void __launch_bounds__(K1_THREADS) halfplane_kernel(int B, int Bpad, 
     const int V = (o < nobs[b]) ? min(nverts[pair], max_verts) : 0;
     if (V <= 0) { c_eta[pair] = make_double4(0.0, 0.0, 0.0, 0.0); return; }
     const double px = pos[(size_t)b * pos_stride], py = pos[(size_t)b * pos_stride + y_off];
-    c_eta[pair] = halfplane_serial<EXACT>(px, py, verts + pair * max_verts, V);
+    c_eta[pair] = WIDE ? halfplane_serial_wide<EXACT>(px, py, verts + pair * max_verts, V)
+                       : halfplane_serial<EXACT>(px, py, verts + pair * max_verts, V);
 }
 
 // Small-batch variant: G lanes per (scenario, obstacle) pair, lane l takes edges l, l+G, ...  With a few thousand
@@ -103,7 +111,10 @@ int launch_halfplanes(int B, int max_obs, int max_verts, const double* pos, int 
     }
     const int Bpad = (B + 31) / 32 * 32;
     const unsigned grid = (unsigned)(((long long)Bpad * max_obs + K1_THREADS - 1) / K1_THREADS);
-    auto kern = fast_geometry ? halfplane_kernel<false> : halfplane_kernel<true>;
+    // 256-bit vertex loads need 32-byte aligned vertex pairs: an aligned base and an even number of slots per ring
+    const bool wide = (reinterpret_cast<uintptr_t>(verts) % 32 == 0) && (max_verts % 2 == 0) && !k1_narrow_loads();
+    auto kern = fast_geometry ? (wide ? halfplane_kernel<false, true> : halfplane_kernel<false, false>)
+                              : (wide ? halfplane_kernel<true, true> : halfplane_kernel<true, false>);
     kern<<<grid, K1_THREADS, 0, st>>>(B, Bpad, max_obs, max_verts, pos, pos_stride, y_off,
                                       reinterpret_cast<const double2*>(verts), nverts, nobs,
                                       reinterpret_cast<double4*>(c_eta));

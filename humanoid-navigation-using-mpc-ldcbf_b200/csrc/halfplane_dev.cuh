@@ -132,6 +132,43 @@ __device__ __forceinline__ double4 halfplane_serial(double px, double py, const 
     return finish_halfplane<EXACT>(px, py, bcx, bcy, cross);
 }
 
+// The same walk with one 256-bit load per TWO vertices (LDG.E.256, sm_100): `ring` must be 32-byte aligned and the
+// slot must hold an even number of vertices (the padded layout with an even max_verts).  Why: with one thread per ring
+// the 32 lanes of a warp read 32 different lines, every 16-byte load costs a wavefront of the L1 data pipe per lane,
+// and ncu put that pipe at 73 % of its peak — the kernel's top limiter, above DRAM (55 %) and the FP64 pipe (44 %).
+// A 32-byte load moves the whole sector a lane touches in one wavefront: half the wavefronts for the same bytes.
+// Same edges in the same order with the same arithmetic as halfplane_serial: bit-identical (c, eta).
+struct __align__(32) VertexPair { double2 a, b; };
+__device__ __forceinline__ VertexPair ldg_pair(const double2* p) {
+    VertexPair r;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(r.a.x), "=d"(r.a.y), "=d"(r.b.x), "=d"(r.b.y) : "l"(p));
+    return r;
+}
+template <bool EXACT>
+__device__ __forceinline__ double4 halfplane_serial_wide(double px, double py, const double2* ring, int V) {
+    double best = KEY_NONE, bcx = 0.0, bcy = 0.0;
+    int cross = 0;
+    VertexPair cur = ldg_pair(ring);
+    const double2 v0 = cur.a;
+    double cx, cy, key;
+    int e = 0;
+    for (; e + 1 < V; e += 2) {                           // edges e and e + 1: both start inside `cur`
+        VertexPair nxt;                                   // in flight while the two edges are evaluated
+        if (e + 2 < V) nxt = ldg_pair(ring + e + 2); else nxt.a = nxt.b = v0;     // the ring closes on vertex 0
+        key = edge_closest<EXACT>(px, py, cur.a, cur.b, cx, cy, cross);
+        if (key_less<EXACT>(key, best)) { best = key; bcx = cx; bcy = cy; }
+        key = edge_closest<EXACT>(px, py, cur.b, nxt.a, cx, cy, cross);
+        if (key_less<EXACT>(key, best)) { best = key; bcx = cx; bcy = cy; }
+        cur = nxt;
+    }
+    if (e < V) {                                          // V odd: the last edge runs from vertex V - 1 back to vertex 0
+        key = edge_closest<EXACT>(px, py, cur.a, v0, cx, cy, cross);
+        if (key_less<EXACT>(key, best)) { best = key; bcx = cx; bcy = cy; }
+    }
+    return finish_halfplane<EXACT>(px, py, bcx, bcy, cross);
+}
+
 // G lanes share a ring: lane l takes edges l, l + G, ..., an xor butterfly merges the partial results by the rule of
 // halfplane_split_kernel (order by the rounded distance, ties towards the lower edge index = the first strict minimum
 // of the serial walk; crossing counts are summed).  Every lane returns the same (c, eta), bit-equal to the serial walk.

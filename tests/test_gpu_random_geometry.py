@@ -74,3 +74,37 @@ def test_lidar_random_polygons_bit_exact():
             o_ho, o_he, o_xy = lidar.cast(pos[b], rings_all[b], rng_, R)
             assert np.array_equal(ho[b], o_ho) and np.array_equal(he[b], o_he), (b, R)
             assert np.array_equal(xy[b], o_xy, equal_nan=True), (b, R)
+
+
+@pytest.mark.parametrize("max_verts", [12, 24, 40])
+def test_halfplanes_wide_loads_equal_narrow_loads(max_verts):
+    """The thread-per-ring kernel reads two vertices per 256-bit load when the vertex pairs are 32-byte aligned (even
+    max_verts, aligned base) and one vertex per 128-bit load otherwise.  Same map at a 32-byte aligned and at a
+    16-byte-only aligned address: bit-identical half-planes (odd and even ring sizes, garbage in the padding), and
+    equal to the oracle."""
+    import ldcbf_b200 as L
+    from ldcbf_b200 import scenarios
+    B, max_obs = 20000, 3                                     # 480 000 lanes of work: the thread-per-ring kernel
+    rs = np.random.default_rng(77 + max_verts)
+    pool = random_rings(rs, 64, max_obs, max_verts)
+    rings_all = [pool[i] for i in rs.integers(0, 64, B)]
+    Q = rs.uniform(-5, 5, (B, 2))
+    verts, nverts, nobs = scenarios.pack_rings(rings_all, max_obs, max_verts)
+    verts = verts.reshape(B, max_obs, max_verts, 2)
+    verts[np.arange(max_verts)[None, None, :] >= nverts[:, :, None]] = 1e300
+    nv, no, q = cu(nverts, torch.int32), cu(nobs, torch.int32), cu(Q)
+    buf = torch.empty(verts.size + 4, dtype=torch.float64, device="cuda")
+    assert buf.data_ptr() % 32 == 0
+    wide_in = buf[:verts.size].view(B, max_obs, max_verts, 2)
+    wide_in.copy_(cu(verts))
+    wide = L.half_planes(q, wide_in, nv, no).clone()
+    narrow_in = buf[2:2 + verts.size].view(B, max_obs, max_verts, 2)     # 16 bytes further: no 256-bit loads
+    assert narrow_in.data_ptr() % 32 == 16
+    narrow_in.copy_(cu(verts))
+    narrow = L.half_planes(q, narrow_in, nv, no)
+    assert torch.equal(wide.view(torch.int64), narrow.view(torch.int64))
+    got = wide.cpu().numpy()
+    for b in rs.choice(B, 400, replace=False):
+        c, eta = halfplane.half_planes(Q[b], rings_all[b])
+        n = len(rings_all[b])
+        assert np.array_equal(got[b, :n, :2], c) and np.array_equal(got[b, :n, 2:], eta, equal_nan=True), b
