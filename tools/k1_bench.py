@@ -22,6 +22,7 @@ def timeit(fn, n=10):
     return sum(ts) / len(ts)
 ms = timeit(lambda: L.half_planes(pos, v, nv, no, c_eta=ce))
 print(f"K1 exact B={B}: {ms*1e3:.1f} us  {984*B/ms/1e6:.0f} GB/s")
+if "--k1-only" in sys.argv: sys.exit(0)
 out = {}
 for flags, name in ((0, "exact"), (FLAG_FAST_GEOMETRY, "fast")):
     prm = L.default_params(0.4, flags=flags)
